@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: SpMM GFLOP/s = 2*nnz*k / tElap
+(aspt/sspmm_128.cu:1406) on a synthetic graph of a README-named shape, with the HBM-roofline
+fraction, the end-to-end (host buffers) number, the CPU baseline and the clocks seen.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload reddit|flickr|yelp|amazon|pubmed]
+                    [--k 128] [--fmt aspt|csr] [--impl reference]
+
+A "step" is one SpMM C = A*B over the whole matrix (every rank: its row-panel shard of A, B
+replicated, no data-path collective).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_K = {"reddit": 128, "flickr": 128, "yelp": 128, "amazon": 128, "pubmed": 32}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default=os.environ.get("FLEX_WORKLOAD", "reddit"))
+    ap.add_argument("--k", type=int, default=0)
+    ap.add_argument("--fmt", default="aspt")
+    ap.add_argument("--order", default="ovo", choices=["ovo", "deg", "rcm", "gor"])
+    ap.add_argument("--shuffle", action="store_true", help="hide the planted block order of the synthetic graph")
+    ap.add_argument("--impl", default="flex_b200", choices=["flex_b200", "reference"])
+    ap.add_argument("--allgather", action="store_true", help="also time the optional NCCL all-gather of C")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cusparse", action="store_true", help="context number: torch.sparse (cuSPARSE) on the same GPU")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(n, nnz, k):
+    """CSR A (rowptr + col,val) + B read once + C written once."""
+    return 4 * (n + 1) + 8 * nnz + 4 * n * k + 4 * n * k
+
+
+def load_workload(name, k, device, shuffle=False):
+    """Returns (rowptr int64, col int64, val f32) torch tensors on `device`."""
+    import torch
+    from flex_b200 import synth
+    if name == "pubmed":
+        import flex_b200 as fx
+        dl = fx.DataLoader(os.path.join(ROOT, "data", "pubmed.csv"), k)
+        rp, c, v = dl.host_csr()
+        return (torch.from_numpy(rp.astype("int64")).to(device), torch.from_numpy(c.astype("int64")).to(device),
+                torch.from_numpy(v.copy()).to(device))
+    return synth.generate(name, device=device, shuffle=shuffle)
+
+
+def panel_shards(rowptr_host, n, world):
+    """nnz-balanced contiguous row ranges aligned to the 128-row panel height."""
+    import numpy as np
+    npanel = (n + 127) // 128
+    pstart = np.minimum(np.arange(npanel + 1) * 128, n)
+    pnnz = rowptr_host[pstart]
+    total = int(pnnz[-1])
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(pnnz, total * r / world)))
+    cuts.append(npanel)
+    cuts = np.maximum.accumulate(np.array(cuts))
+    return [(int(pstart[cuts[r]]), int(pstart[cuts[r + 1]])) for r in range(world)]
+
+
+class ClockSampler(threading.Thread):
+    """NVML clocks / throttle reasons every few ms while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag, self.ok = [], set(), False, False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def summary(self):
+        import statistics
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_baseline(rp, c, v, Bh, k, budget_s=12.0):
+    """The reference's CPU SpMM (aspt/sspmm_128.cu:1415-1422) restated in oracle/, all host
+    threads, on a bounded row-prefix sample of the same matrix."""
+    import numpy as np
+    from oracle import orc
+    orc.build()
+    n = len(rp) - 1
+    cores = orc.orc_num_threads() if hasattr(orc, "orc_num_threads") else orc.lib().orc_num_threads()
+    # probe on ~2% of the nz to size the sample
+    probe_rows = int(np.searchsorted(rp, rp[-1] * 0.02)) or 1
+    sub = rp[:probe_rows + 1].copy()
+    t0 = time.perf_counter()
+    orc.spmm_omp(sub, c[:sub[-1]], v[:sub[-1]], Bh)
+    t_probe = max(time.perf_counter() - t0, 1e-6)
+    rate = sub[-1] / t_probe
+    want_nnz = min(int(rp[-1]), int(rate * budget_s))
+    rows = int(np.searchsorted(rp, want_nnz, side="right")) - 1
+    rows = max(1, min(n, rows))
+    sub = rp[:rows + 1].copy()
+    out = np.empty((rows, k), np.float32)
+    t0 = time.perf_counter()
+    orc.spmm_omp(sub, c[:sub[-1]], v[:sub[-1]], Bh, out=out)
+    dt = time.perf_counter() - t0
+    nnz_s = int(sub[-1])
+    return {"value": 2.0 * nnz_s * k / dt / 1e9, "unit": "GFLOP/s", "cores": int(cores), "kind": "port",
+            "sample": f"rows [0,{rows}) of the workload ({nnz_s} nz, {100.0 * nnz_s / int(rp[-1]):.1f}% of nnz), "
+                      f"1 pass, {dt:.2f} s, OpenMP row-parallel restatement of aspt/sspmm_128.cu:1415-1422"}
+
+
+def run_reference(args, k):
+    """--impl reference: the reference's own CPU SpMM (oracle port) on the host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import orc
+    orc.build()
+    rp, c, v = load_workload(args.workload, k, "cpu", args.shuffle)
+    rp, c, v = rp.numpy().astype(np.uint32), c.numpy().astype(np.uint32), v.numpy()
+    n, nnz = len(rp) - 1, len(c)
+    from flex_b200 import synth
+    Bh = synth.dense_B(n, k).numpy()
+    cores = orc.lib().orc_num_threads()
+    # bounded sample: a row prefix that takes ~1.5 s per step
+    probe_rows = int(np.searchsorted(rp, rp[-1] * 0.02)) or 1
+    sub = rp[:probe_rows + 1].copy()
+    t0 = time.perf_counter()
+    orc.spmm_omp(sub, c[:sub[-1]], v[:sub[-1]], Bh)
+    rate = sub[-1] / max(time.perf_counter() - t0, 1e-6)
+    budget = min(1.5, 150.0 / max(1, args.steps + args.warmup))
+    rows = max(1, min(n, int(np.searchsorted(rp, min(nnz, int(rate * budget)), side="right")) - 1))
+    sub = rp[:rows + 1].copy()
+    nnz_s = int(sub[-1])
+    out = np.empty((rows, k), np.float32)
+    for _ in range(args.warmup):
+        orc.spmm_omp(sub, c[:nnz_s], v[:nnz_s], Bh, out=out)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.spmm_omp(sub, c[:nnz_s], v[:nnz_s], Bh, out=out)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    val = 2.0 * nnz_s * k / dt / 1e9
+    sample = (f"rows [0,{rows}) of the workload ({nnz_s} nz, {100.0 * nnz_s / nnz:.1f}% of nnz) per step; "
+              f"OpenMP restatement of the reference CPU SpMM aspt/sspmm_128.cu:1415-1422 (the reference embeds its "
+              f"CPU loop in a CUDA main(), so it cannot be timed alone)")
+    line = {"impl": "reference", "metric": "SpMM GFLOP/s (2*nnz*k/tElap)", "value": val, "unit": "GFLOP/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, k, n, nnz),
+            "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": int(cores), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, k, n, nnz):
+    return {"workload": f"{args.workload}-shape" if args.workload != "pubmed" else "pubmed.csv", "n": n, "nnz": nnz,
+            "k": k, "format": args.fmt, "order": args.order, "shuffled_ids": bool(args.shuffle),
+            "l2_policy": "inputs larger than L2 (A+B+C bytes > 126 MB)" if algorithmic_bytes(n, nnz, k) > 126e6
+            else "whole problem fits L2: L2 flushed by a 256 MB write between timed steps",
+            "parallelism": f"row-panel shards x{args.gpus}, B replicated"}
+
+
+def main():
+    args = parse()
+    k = args.k or DEFAULT_K.get(args.workload, 128)
+    if args.impl == "reference":
+        return run_reference(args, k)
+
+    import numpy as np
+    import torch
+    import flex_b200 as fx
+    from flex_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        print("bench.py --gpus N>1 must be launched by torch.distributed.run", file=sys.stderr)
+        return 2
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    rp, c, v = load_workload(args.workload, k, dev, args.shuffle)
+    n, nnz = rp.numel() - 1, c.numel()
+    rp_host = rp.cpu().numpy()
+    rp32, c32 = rp.to(torch.int32), c.to(torch.int32)
+    need_host = args.order != "ovo"
+    if need_host:
+        dl0 = fx.DataLoader.from_arrays(rp_host.astype(np.uint32), c.cpu().numpy().astype(np.uint32), v.cpu().numpy(), k,
+                                        args.workload + ".csv")
+        dl = dl0.reorder({"deg": fx.FX_ORDER_DEG, "rcm": fx.FX_ORDER_RCM, "gor": fx.FX_ORDER_GOR}[args.order])
+        rp_host = dl.rowPtr.astype(np.int64)
+    else:
+        dl = fx.DataLoader.from_device(n, nnz, rp32.data_ptr(), c32.data_ptr(), v.data_ptr(), k, args.workload + ".csv")
+    shards = panel_shards(rp_host, n, world)
+    lo, hi = shards[rank]
+    mat = fx.Mat(dl, fmt=args.fmt, row_begin=lo, row_end=hi)
+    tpre = [mat.tPre_ms] + [mat.rebuild() for _ in range(3)]
+    B = synth.dense_B(n, k, device=dev)
+    Cd = torch.empty((hi - lo, k), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    small = algorithmic_bytes(n, nnz, k) <= 126e6
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev) if small else None
+
+    def step():
+        mat.spmm(B.data_ptr(), Cd.data_ptr(), k, stream=stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = fx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if small:
+        # problem fits in L2: flush between steps and sum per-step event times
+        tot = 0.0
+        for _ in range(args.steps):
+            flush.fill_(1.0)
+            e0.record(); step(); e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        ms = tot
+    else:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+    launches = fx.launch_count() - l0
+    sync_all()
+    # keep the device busy long enough for the clock sampler to see the kernel under load
+    t_end = time.time() + 0.5
+    while len(sampler.samples) < 50 and time.time() < t_end:
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = t.item() / args.steps
+
+    # end to end through the public call with HOST buffers (pinned): H2D B, kernels, D2H C
+    Bh = torch.empty((n, k), dtype=torch.float32).pin_memory()
+    Bh.copy_(B)
+    Ch = torch.empty((hi - lo, k), dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
+    mat.spmm_host(Bh.numpy(), out=Ch.numpy())
+    sync_all()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(e2e_steps):
+        mat.spmm_host(Bh.numpy(), out=Ch.numpy())
+        dev_ms += mat.last_total_ms
+    e2e_ms = torch.tensor([dev_ms / e2e_steps], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = e2e_ms.item()
+
+    ag_ms = None
+    if args.allgather and dist is not None:
+        rows = [s[1] - s[0] for s in shards]
+        outs = [torch.empty((r, k), dtype=torch.float32, device=dev) for r in rows]
+        dist.all_gather(outs, Cd)  # warm-up
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        dist.all_gather(outs, Cd)
+        a1.record()
+        a1.synchronize()
+        ag = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ag, op=dist.ReduceOp.MAX)
+        ag_ms = ag.item()
+
+    if rank == 0:
+        flops = 2.0 * nnz * k
+        value = flops / (ms_per_step * 1e-3) / 1e9
+        peak, peak_src = peaks()
+        # roofline for the dominant kernel: every rank streams its share of A and C plus (at most) all of B
+        loc_nnz = int(rp_host[hi] - rp_host[lo])
+        abytes = 4 * (hi - lo + 1) + 8 * loc_nnz + 4 * n * k + 4 * (hi - lo) * k
+        achieved = abytes / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": "SpMM GFLOP/s (2*nnz*k/tElap)", "value": value, "unit": "GFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic" if args.workload != "pubmed" else "data/pubmed.csv",
+            "config": workload_config(args, k, n, nnz),
+            "tPre_ms": min(tpre), "tPre_over_tElap": min(tpre) / ms_per_step,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": abytes,
+                         "kernel": "k_spmm_panel (+ k_spmm_special for 512-nz chunks of long rows); timed together"},
+            "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(4 * n * k), "d2h_bytes_per_step": int(4 * (hi - lo) * k)},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+        }
+        if ag_ms is not None:
+            line["allgather_ms"] = ag_ms
+        if args.cusparse:
+            A = torch.sparse_csr_tensor(rp, c, v, size=(n, n))
+            for _ in range(3):
+                torch.sparse.mm(A, B)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(10):
+                torch.sparse.mm(A, B)
+            c1.record(); c1.synchronize()
+            line["cusparse_context_gflops"] = flops / (c0.elapsed_time(c1) / 10 * 1e-3) / 1e9
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(rp_host.astype(np.uint32), c32.cpu().numpy().view(np.uint32),
+                                                v.cpu().numpy(), Bh.numpy(), k)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main() or 0)

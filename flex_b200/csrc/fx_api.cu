@@ -1,0 +1,240 @@
+// fx_api.cu -- extern "C" entry points for build / SpMM / validation (include/flexb200.h).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+
+#include "fx_common.cuh"
+
+namespace {
+
+int check_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    fx::set_error("no CUDA device: %s (libflexb200 has no CPU path)", cudaGetErrorString(e));
+    return FX_ERR_CUDA;
+  }
+  return FX_OK;
+}
+
+int time_region(fx_tiles* t, cudaStream_t s, float* ms, int (*fn)(fx_tiles*, cudaStream_t)) {
+  FX_CUDA(cudaEventRecord(t->ev0, s));
+  int rc = fn(t, s);
+  if (rc != FX_OK) return rc;
+  FX_CUDA(cudaEventRecord(t->ev1, s));
+  FX_CUDA(cudaEventSynchronize(t->ev1));
+  if (ms) FX_CUDA(cudaEventElapsedTime(ms, t->ev0, t->ev1));
+  return FX_OK;
+}
+
+int build_dispatch(fx_tiles* t, cudaStream_t s) {
+  switch (t->format) {
+    case FX_FMT_CSR: return FX_OK;
+    case FX_FMT_ASPT: return fx::aspt_build(t, s);
+    default: fx::set_error("format %d not built by this entry point", t->format); return FX_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace
+
+extern "C" int fx_build(const fx_matrix* m, const fx_build_opts* opts, fx_tiles** out, float* tPre_ms) {
+  FX_REQUIRE(m && out, FX_ERR_ARG, "fx_build: null argument");
+  int rc = check_device();
+  if (rc != FX_OK) return rc;
+  rc = fx::ensure_device(m);
+  if (rc != FX_OK) return rc;
+  auto t = new fx_tiles();
+  t->mat = m;
+  if (opts) t->opts = *opts;
+  t->format = opts ? opts->format : FX_FMT_ASPT;
+  t->k = (int)m->k;
+  t->row_begin = t->opts.row_begin;
+  t->row_end = t->opts.row_end;
+  if (t->row_begin == 0 && t->row_end == 0) t->row_end = (int)m->n;
+  if (t->row_begin < 0 || t->row_end > m->n || t->row_begin > t->row_end) {
+    delete t;
+    fx::set_error("fx_build: bad row range");
+    return FX_ERR_ARG;
+  }
+  t->nnz_local = (int64_t)m->rowptr[t->row_end] - (int64_t)m->rowptr[t->row_begin];
+  auto fail = [&](int code) { fx_tiles_free(t); return code; };
+  if (cudaEventCreate(&t->ev0) != cudaSuccess || cudaEventCreate(&t->ev1) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost(&t->stats_host, sizeof(unsigned long long) * 8) != cudaSuccess) {
+    fx::set_error("fx_build: event/stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(FX_ERR_CUDA);
+  }
+  if (t->format == FX_FMT_ASPT) {
+    fx_aspt_dev& a = t->aspt;
+    const int nloc = t->row_end - t->row_begin;
+    a.n = nloc;
+    a.nr = (nloc + 127) / 128 * 128;
+    a.npanel = a.nr / 128;
+    a.ne = (int)t->nnz_local;
+    a.row0 = t->row_begin;
+    a.BW = t->opts.bw ? t->opts.bw : (m->k >= 64 ? 128 : 256);  // sspmm_128.cu:34 vs sspmm_32.cu:33
+    if (a.BW != 128 && a.BW != 256) { fx::set_error("bw must be 128 or 256"); return fail(FX_ERR_ARG); }
+    rc = fx::aspt_carve(t, m->n);
+    if (rc != FX_OK) return fail(rc);
+  } else if (t->format != FX_FMT_CSR) {
+    fx::set_error("fx_build: format %d is built through fx_flex_build", t->format);
+    return fail(FX_ERR_UNSUPPORTED);
+  }
+  rc = time_region(t, t->own_stream, tPre_ms, build_dispatch);
+  if (rc != FX_OK) return fail(rc);
+  *out = t;
+  return FX_OK;
+}
+
+extern "C" int fx_rebuild(fx_tiles* t, float* tPre_ms) {
+  FX_REQUIRE(t, FX_ERR_ARG, "fx_rebuild: null");
+  return time_region(t, t->own_stream, tPre_ms, build_dispatch);
+}
+
+extern "C" void fx_tiles_free(fx_tiles* t) {
+  if (!t) return;
+  t->arena.release();
+  if (t->ev0) cudaEventDestroy(t->ev0);
+  if (t->ev1) cudaEventDestroy(t->ev1);
+  if (t->own_stream) cudaStreamDestroy(t->own_stream);
+  if (t->stats_host) cudaFreeHost(t->stats_host);
+  cudaFree(t->B_stage_dev); cudaFree(t->C_stage_dev);
+  if (t->B_pinned) cudaFreeHost(t->B_pinned);
+  if (t->C_pinned) cudaFreeHost(t->C_pinned);
+  delete t;
+}
+
+template <class T>
+static int d2h(std::vector<T>& dst, const void* src, size_t count) {
+  dst.resize(count);
+  if (count) FX_CUDA(cudaMemcpy(dst.data(), src, sizeof(T) * count, cudaMemcpyDeviceToHost));
+  return FX_OK;
+}
+
+extern "C" int fx_tiles_export_aspt(fx_tiles* t, fx_aspt_arrays* o) {
+  FX_REQUIRE(t && o && t->format == FX_FMT_ASPT, FX_ERR_ARG, "fx_tiles_export_aspt: not an ASpT handle");
+  const fx_aspt_dev& a = t->aspt;
+  FX_CUDA(cudaDeviceSynchronize());
+  int rc;
+  const size_t nd = a.num_dense;
+  if ((rc = d2h(t->h_chk, a.mcsr_chk, a.npanel))) return rc;
+  if ((rc = d2h(t->h_cnt, a.mcsr_cnt, a.npanel + 1))) return rc;
+  if ((rc = d2h(t->h_e, a.mcsr_e_use, (size_t)128 * (nd + a.npanel) + 1))) return rc;
+  if ((rc = d2h(t->h_list, a.mcsr_list, nd * a.BW))) return rc;
+  if ((rc = d2h(t->h_baddr, a.baddr, nd))) return rc;
+  if ((rc = d2h(t->h_saddr, a.saddr, nd))) return rc;
+  if ((rc = d2h(t->h_csr_e, a.csr_e_use, a.ne))) return rc;
+  if ((rc = d2h(t->h_csr_ev, a.csr_ev_use, a.ne))) return rc;
+  if (a.aliased) {
+    t->h_perm.resize(a.ne);
+    for (int i = 0; i < a.ne; ++i) t->h_perm[i] = i;
+  } else if ((rc = d2h(t->h_perm, a.perm, a.ne))) return rc;
+  // the reference only materialises the special lists when vari >= 200 (:1319-1328)
+  const int sp = a.vari >= 200 ? a.special_p : 0;
+  if ((rc = d2h(t->h_special, a.special, sp))) return rc;
+  if ((rc = d2h(t->h_special2, a.special2, sp))) return rc;
+  o->n = a.n; o->nr = a.nr; o->npanel = a.npanel; o->ne = a.ne; o->BH = 128; o->BW = a.BW;
+  o->num_dense = a.num_dense; o->any_flag = a.any_flag; o->regime = a.regime; o->special_p = sp;
+  o->S1 = a.S1; o->S2 = a.S2; o->avg = a.avg; o->vari = a.vari;
+  o->mcsr_chk = t->h_chk.data(); o->mcsr_cnt = t->h_cnt.data(); o->mcsr_e = t->h_e.data();
+  o->mcsr_list = t->h_list.data(); o->baddr = t->h_baddr.data(); o->saddr = t->h_saddr.data();
+  o->perm = t->h_perm.data(); o->csr_e = t->h_csr_e.data(); o->csr_ev = t->h_csr_ev.data();
+  o->special = t->h_special.data(); o->special2 = t->h_special2.data();
+  return FX_OK;
+}
+
+static int spmm_dispatch(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s) {
+  const fx_matrix* m = t->mat;
+  if (t->format == FX_FMT_CSR || k % 4 != 0) {
+    // raw CSR over the shard's rows (run_ge_spmm path flex.cu:4285; "ssparse" regime :629)
+    return fx::spmm_csr(m->rowptr_dev + t->row_begin, m->col_dev, m->val_dev, t->row_end - t->row_begin, B, C, k, s);
+  }
+  if (t->format == FX_FMT_ASPT) return fx::spmm_aspt(t, B, C, k, s);
+  fx::set_error("fx_spmm: format %d has its own entry point", t->format);
+  return FX_ERR_UNSUPPORTED;
+}
+
+extern "C" int fx_spmm(const fx_tiles* t, const float* B_dev, float* C_dev, int k, void* stream, float* tElap_ms) {
+  FX_REQUIRE(t && B_dev && C_dev && k > 0, FX_ERR_ARG, "fx_spmm: bad argument");
+  FX_REQUIRE((int64_t)t->mat->n * k / 4 < (1ll << 32), FX_ERR_UNSUPPORTED, "n*k too large for 32-bit float4 offsets");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!tElap_ms) return spmm_dispatch(t, B_dev, C_dev, k, s);
+  fx_tiles* tt = const_cast<fx_tiles*>(t);
+  FX_CUDA(cudaEventRecord(tt->ev0, s));
+  int rc = spmm_dispatch(t, B_dev, C_dev, k, s);
+  if (rc != FX_OK) return rc;
+  FX_CUDA(cudaEventRecord(tt->ev1, s));
+  FX_CUDA(cudaEventSynchronize(tt->ev1));
+  FX_CUDA(cudaEventElapsedTime(tElap_ms, tt->ev0, tt->ev1));
+  return FX_OK;
+}
+
+extern "C" int fx_spmm_host(const fx_tiles* tc, const float* B_host, float* C_host, int k, float* total_ms,
+                            float* tElap_ms) {
+  FX_REQUIRE(tc && B_host && C_host && k > 0, FX_ERR_ARG, "fx_spmm_host: bad argument");
+  fx_tiles* t = const_cast<fx_tiles*>(tc);
+  const size_t nB = (size_t)t->mat->n * k, nC = (size_t)(t->row_end - t->row_begin) * k;
+  if (t->stage_elems < std::max(nB, nC)) {
+    cudaFree(t->B_stage_dev); cudaFree(t->C_stage_dev);
+    t->B_stage_dev = t->C_stage_dev = nullptr;
+    t->stage_elems = 0;
+    FX_CUDA(cudaMalloc(&t->B_stage_dev, sizeof(float) * std::max<size_t>(nB, 1)));
+    FX_CUDA(cudaMalloc(&t->C_stage_dev, sizeof(float) * std::max<size_t>(nC, 1)));
+    t->stage_elems = std::max(nB, nC);
+  }
+  cudaStream_t s = t->own_stream;
+  cudaEvent_t e0, e1, k0, k1;
+  FX_CUDA(cudaEventCreate(&e0)); FX_CUDA(cudaEventCreate(&e1));
+  FX_CUDA(cudaEventCreate(&k0)); FX_CUDA(cudaEventCreate(&k1));
+  FX_CUDA(cudaEventRecord(e0, s));
+  FX_CUDA(cudaMemcpyAsync(t->B_stage_dev, B_host, sizeof(float) * nB, cudaMemcpyHostToDevice, s));
+  FX_CUDA(cudaEventRecord(k0, s));
+  int rc = spmm_dispatch(t, t->B_stage_dev, t->C_stage_dev, k, s);
+  if (rc != FX_OK) return rc;
+  FX_CUDA(cudaEventRecord(k1, s));
+  FX_CUDA(cudaMemcpyAsync(C_host, t->C_stage_dev, sizeof(float) * nC, cudaMemcpyDeviceToHost, s));
+  FX_CUDA(cudaEventRecord(e1, s));
+  FX_CUDA(cudaEventSynchronize(e1));
+  if (total_ms) FX_CUDA(cudaEventElapsedTime(total_ms, e0, e1));
+  if (tElap_ms) FX_CUDA(cudaEventElapsedTime(tElap_ms, k0, k1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(k0); cudaEventDestroy(k1);
+  return FX_OK;
+}
+
+extern "C" int fx_permute_rows(const fx_matrix* m, const float* B_dev, float* shadowB_dev, int k, void* stream) {
+  FX_REQUIRE(m && B_dev && shadowB_dev, FX_ERR_ARG, "fx_permute_rows: bad argument");
+  if (int rc = fx::ensure_device(m)) return rc;
+  return fx::permute_rows(m->vo_mp_dev, m->n, k, B_dev, shadowB_dev, false, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fx_unpermute_rows(const fx_matrix* m, const float* C_dev, float* C_out_dev, int k, void* stream) {
+  FX_REQUIRE(m && C_dev && C_out_dev, FX_ERR_ARG, "fx_unpermute_rows: bad argument");
+  if (int rc = fx::ensure_device(m)) return rc;
+  return fx::permute_rows(m->vo_mp_dev, m->n, k, C_dev, C_out_dev, true, static_cast<cudaStream_t>(stream));
+}
+
+// resCheck (flex.cu:4155-4213) + ASpT validator (aspt/sspmm_128.cu:1425-1446) + the 1e-5 contract
+extern "C" int fx_check(const float* gold, const float* res, int64_t n, int k, const uint32_t* rowptr, fx_report* rep) {
+  FX_REQUIRE(gold && res && rep, FX_ERR_ARG, "fx_check: null");
+  int64_t flex = 0, tight = 0, aspt = 0;
+  double max_err = 0;
+  for (int64_t r = 0; r < n; ++r) {
+    const int rnnz = rowptr ? (int)(rowptr[r + 1] - rowptr[r]) : 1;
+    const double tol = (double)FLT_EPSILON * rnnz * 4;
+    for (int j = 0; j < k; ++j) {
+      const float g = gold[r * k + j], x = res[r * k + j];
+      const double d = std::fabs((double)g - (double)x);
+      const double err = std::fabs(g) < 1 ? d : d / std::fabs(g);
+      if (!(err <= tol)) flex++;
+      if (err > max_err) max_err = err;
+      const float p1 = std::fabs(g), p2 = std::fabs(x);
+      if (std::fabs(p1 - p2) / std::max(p1, p2) > 0.01f) aspt++;
+      if (!(d <= 1e-5 * std::max(1.0, (double)std::fabs(g)))) tight++;
+    }
+  }
+  rep->errs_flex = flex;
+  rep->errs_tight = tight;
+  rep->errs_aspt_pct = (n * k) != 0 ? (double)aspt / (double)(n * k) * 100 : 0;
+  rep->max_err = max_err;
+  return FX_OK;
+}

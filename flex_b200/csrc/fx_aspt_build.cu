@@ -1,0 +1,495 @@
+// fx_aspt_build.cu -- GPU builder of the ASpT dense/sparse tile format.
+//
+// Produces, bit for bit, the layout the reference's pre-process section builds
+// (aspt/sspmm_128.cu:1207-1333 with kernels :831-1087) under the canonical tie-breaks
+// (heavy columns take slots in ascending column order; a row's nz keep their column order
+// inside each group), but by a different route that suits a B200:
+//   * the reference sorts every panel's nz by column (bb_segsort #1) to find heavy columns and
+//     then sorts every row by tile id (bb_segsort #2); here heavy columns are found by counting
+//     into an L2-resident per-CTA column counter array (one atomic per nz), only the few heavy
+//     columns of a panel are sorted (shared-memory bitonic network), and rows are partitioned by
+//     a warp-level stable counting scatter (match_any + popc) -- no full sort of the nz at all;
+//   * no allocation, no host round trip except one 64-byte read of the statistics at the end
+//     (the reference does ~20 cudaMalloc/cudaFree and 5 blocking copies inside tPre).
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+#include <cooperative_groups/scan.h>
+
+#include "fx_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int BH = 128;          // panel height            aspt/sspmm_128.cu:33
+constexpr int THRESHOLD = 16;    // heavy column threshold  :32
+constexpr int SC_SIZE = 2048;    // detect histogram        :46
+constexpr int STHRESHOLD = 512;  // long-row chunk          :44
+constexpr int SPARSE_KEY = 30000;  // :890
+constexpr int OCC_SIZE = 1024;   // MCSR_CNT_SIZE :895
+constexpr int SORT_SMEM_CAP = 8192;  // heavy columns sorted in shared memory up to this many
+
+// ---- K0: padded local row pointer ---------------------------------------------------------
+__global__ void k_pad_rowptr(const uint32_t* __restrict__ rowptr, int row0, int nloc, int nr, int ne,
+                             int* __restrict__ csr_v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= nr) csr_v[i] = i <= nloc ? (int)(rowptr[row0 + i] - rowptr[row0]) : ne;
+}
+
+// ---- K1: dense_block_detect (:831-868) ----------------------------------------------------
+__global__ void __launch_bounds__(256) k_detect(const int* __restrict__ csr_v, const uint32_t* __restrict__ col,
+                                                int min_occ, int* __restrict__ chk,
+                                                unsigned long long* __restrict__ stats) {
+  __shared__ int hist[SC_SIZE];
+  __shared__ int total;
+  const int p = blockIdx.x;
+  for (int i = threadIdx.x; i < SC_SIZE; i += blockDim.x) hist[i] = 0;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  const int lb = csr_v[p * BH], ub = csr_v[(p + 1) * BH];
+  for (int i = lb + threadIdx.x; i < ub; i += blockDim.x) atomicAdd(&hist[col[i] & (SC_SIZE - 1)], 1);
+  __syncthreads();
+  int r = 0;
+  for (int i = threadIdx.x; i < SC_SIZE; i += blockDim.x) r += hist[i] >= THRESHOLD;
+  r = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), r, cg::plus<int>());
+  if ((threadIdx.x & 31) == 0 && r) atomicAdd(&total, r);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int f = total >= min_occ;
+    chk[p] = f;
+    if (f) atomicOr(&stats[4], 1ull);
+  }
+}
+
+// ---- K2: heavy columns, slot depths, tile count and per-nz tile id of flagged panels -----
+// (mcsr_cnt_calc :896-925 + key2_marking :929-981 without the panel sort)
+__device__ __forceinline__ void cmpswap(unsigned long long& a, unsigned long long& b) {
+  if (a > b) { unsigned long long t = a; a = b; b = t; }
+}
+
+// normalised bitonic network: every comparator moves the minimum to the lower index, so indices
+// >= n behave as +inf padding and arbitrary n sorts correctly.
+__device__ void block_sort_u64(unsigned long long* a, int n) {
+  int N = 1;
+  while (N < n) N <<= 1;
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      int j = i ^ (k - 1);
+      if (j > i && j < n) cmpswap(a[i], a[j]);
+    }
+    __syncthreads();
+    for (int s = k >> 2; s > 0; s >>= 1) {
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        int j = i ^ s;
+        if (j > i && j < n) cmpswap(a[i], a[j]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512) k_heavy(const int* __restrict__ csr_v, const uint32_t* __restrict__ col,
+                                               const int* __restrict__ chk, int npanel, int BW, int min_occ,
+                                               int ncols, unsigned* __restrict__ cnt_all,
+                                               unsigned long long* __restrict__ heavy_all, int* __restrict__ nheavy,
+                                               int* __restrict__ tcount, uint16_t* __restrict__ key2) {
+  extern __shared__ unsigned long long skeys[];  // SORT_SMEM_CAP
+  __shared__ int occ[OCC_SIZE];
+  __shared__ int gstart[256];
+  __shared__ int s_nh, s_tp;
+  unsigned* cnt = cnt_all + (size_t)blockIdx.x * ncols;
+  const int wmask = BW - 1;
+  for (int p = blockIdx.x; p < npanel; p += gridDim.x) {
+    if (!chk[p]) continue;  // uniform
+    const int lb = csr_v[p * BH], ub = csr_v[(p + 1) * BH];
+    unsigned long long* heavy = heavy_all + (lb / THRESHOLD + p);
+    if (threadIdx.x == 0) { s_nh = 0; s_tp = 0; }
+    for (int i = threadIdx.x; i < OCC_SIZE; i += blockDim.x) occ[i] = 0;
+    __syncthreads();
+    // pass 1: count columns; the 16th hit of a column registers it as heavy
+    for (int e = lb + threadIdx.x; e < ub; e += blockDim.x) {
+      unsigned c = col[e];
+      unsigned old = atomicAdd(&cnt[c], 1u);
+      if (old == THRESHOLD - 1) {
+        int pos = atomicAdd(&s_nh, 1);
+        heavy[pos] = ((unsigned long long)(c & wmask) << 32) | c;
+      }
+    }
+    __syncthreads();
+    const int nh = s_nh;
+    // sort heavy columns by (slot width, column): ascending column inside each slot = canonical
+    unsigned long long* keys = heavy;
+    if (nh <= SORT_SMEM_CAP) {
+      for (int i = threadIdx.x; i < nh; i += blockDim.x) skeys[i] = heavy[i];
+      keys = skeys;
+    }
+    __syncthreads();
+    block_sort_u64(keys, nh);
+    for (int i = threadIdx.x; i < nh; i += blockDim.x) {
+      int w = (int)(keys[i] >> 32);
+      if (i == 0 || (int)(keys[i - 1] >> 32) != w) gstart[w] = i;
+    }
+    __syncthreads();
+    // occ'[d+1] = #slots with more than d heavy columns (:915-916); occ'[0] = BW
+    for (int i = threadIdx.x; i < nh; i += blockDim.x) {
+      int d = i - gstart[(int)(keys[i] >> 32)];
+      if (d + 1 < OCC_SIZE) atomicAdd(&occ[d + 1], 1);
+    }
+    if (threadIdx.x == 0) occ[0] = BW;
+    __syncthreads();
+    for (int t = threadIdx.x; t < OCC_SIZE - 1; t += blockDim.x)
+      if (occ[t] >= min_occ && occ[t + 1] < min_occ) s_tp = t;  // :921-922 (unique t: occ is non-increasing)
+    __syncthreads();
+    const int tp = s_tp;
+    // publish (column, depth); mark the columns that made it into a tile in the counter array
+    for (int i = threadIdx.x; i < nh; i += blockDim.x) {
+      unsigned long long kk = keys[i];
+      unsigned c = (unsigned)kk;
+      int d = i - gstart[(int)(kk >> 32)];
+      if (d < tp) cnt[c] = 0x80000000u | (unsigned)d;
+      heavy[i] = ((unsigned long long)(unsigned)d << 32) | c;  // read as int2 {c, depth}
+    }
+    if (threadIdx.x == 0) { nheavy[p] = nh; tcount[p] = tp; }
+    __syncthreads();
+    // pass 2: tile id of every nz (key2, :971-978); pass 3 restores the counters to zero
+    if (tp > 0) {
+      for (int e = lb + threadIdx.x; e < ub; e += blockDim.x) {
+        unsigned x = cnt[col[e]];
+        key2[e] = (x & 0x80000000u) ? (uint16_t)(x & 0xffffu) : (uint16_t)SPARSE_KEY;
+      }
+      __syncthreads();
+    }
+    for (int e = lb + threadIdx.x; e < ub; e += blockDim.x) cnt[col[e]] = 0u;
+    __syncthreads();
+  }
+}
+
+// ---- K3: mcsr_cnt prefix (host loop :1260-1266 moved to the device) ------------------------
+__global__ void __launch_bounds__(1024) k_scan_tcount(const int* __restrict__ tcount, int npanel,
+                                                      int* __restrict__ mcsr_cnt,
+                                                      unsigned long long* __restrict__ stats) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  __shared__ int maxtp;
+  auto warp = cg::tiled_partition<32>(cg::this_thread_block());
+  if (threadIdx.x == 0) { carry_s = 0; mcsr_cnt[0] = 0; maxtp = 0; }
+  __syncthreads();
+  int mymax = 0;
+  for (int base = 0; base < npanel; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    int t = i < npanel ? tcount[i] : 0;
+    mymax = max(mymax, t);
+    int v = i < npanel ? t + 1 : 0;
+    int inc = cg::inclusive_scan(warp, v);
+    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int ws = threadIdx.x < (blockDim.x >> 5) ? warp_sum[threadIdx.x] : 0;
+      int wi = cg::inclusive_scan(warp, ws);
+      warp_sum[threadIdx.x] = wi - ws;
+    }
+    __syncthreads();
+    int total = carry_s + warp_sum[threadIdx.x >> 5] + inc;
+    if (i < npanel) mcsr_cnt[i + 1] = total;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = total;
+    __syncthreads();
+  }
+  mymax = cg::reduce(warp, mymax, cg::greater<int>());
+  if ((threadIdx.x & 31) == 0) atomicMax(&maxtp, mymax);
+  __syncthreads();
+  if (threadIdx.x == 0) { stats[3] = (unsigned long long)(carry_s - npanel); stats[5] = (unsigned long long)maxtp; }
+}
+
+// ---- K4: slot lists, per-row group offsets, stable partition of the nz ---------------------
+// (key2_marking's list writes :958-959,946-949; bb_segsort#2 :1282; fill_mcsre :1006-1038;
+//  porting :1040-1048; the length statistics of cal_vari :1050-1073)
+constexpr int FILL_WARPS = 8;
+__global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(
+    const int* __restrict__ csr_v, const uint32_t* __restrict__ col, const float* __restrict__ val,
+    const int* __restrict__ tcount, const int* __restrict__ mcsr_cnt, const int2* __restrict__ heavy_all,
+    const int* __restrict__ nheavy, const uint16_t* __restrict__ key2, int npanel, int BW, int ne,
+    int* __restrict__ mcsr_e, int* __restrict__ mcsr_list, int* __restrict__ baddr, int* __restrict__ saddr,
+    int* __restrict__ perm, int* __restrict__ csr_e, float* __restrict__ csr_ev, int* __restrict__ spec_cnt,
+    unsigned long long* __restrict__ stats) {
+  __shared__ int hist[FILL_WARPS][OCC_SIZE];
+  const int p = blockIdx.x;
+  const int tp = tcount[p], cnt0 = mcsr_cnt[p], delta = tp + 1, g0 = cnt0 - p;
+  const int wmask = BW - 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (tp > 0) {
+    for (int i = threadIdx.x; i < tp * BW; i += blockDim.x) mcsr_list[(size_t)g0 * BW + i] = -1;  // memset -1 :1128
+    for (int i = threadIdx.x; i < tp; i += blockDim.x) { baddr[g0 + i] = p; saddr[g0 + i] = i; }
+    __syncthreads();
+    const int2* heavy = heavy_all + (csr_v[p * BH] / THRESHOLD + p);
+    const int nh = nheavy[p];
+    for (int i = threadIdx.x; i < nh; i += blockDim.x) {
+      int2 h = heavy[i];
+      if (h.y < tp) mcsr_list[(size_t)(g0 + h.y) * BW + (h.x & wmask)] = h.x;
+    }
+  }
+  long long s1 = 0, s2 = 0;
+  int chunks = 0;
+  for (int r = warp; r < BH; r += FILL_WARPS) {
+    const int row = p * BH + r;
+    const int rs = csr_v[row], re = csr_v[row + 1];
+    const int base = cnt0 * BH + r * delta;
+    int len;
+    if (tp == 0) {
+      if (lane == 0) mcsr_e[base] = rs;
+      for (int e = rs + lane; e < re; e += 32) { perm[e] = e; csr_e[e] = (int)col[e]; csr_ev[e] = val[e]; }
+      len = re - rs;
+    } else {
+      int* h = hist[warp];
+      for (int g = lane; g < delta; g += 32) h[g] = 0;
+      __syncwarp();
+      for (int e = rs + lane; e < re; e += 32) {
+        int g = key2[e];
+        g = g == SPARSE_KEY ? tp : g;
+        atomicAdd(&h[g], 1);
+      }
+      __syncwarp();
+      // exclusive scan of the group sizes -> group starts
+      int carry = 0;
+      for (int g0i = 0; g0i < delta; g0i += 32) {
+        int g = g0i + lane;
+        int v = g < delta ? h[g] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        int ex = carry + inc - v;
+        if (g < delta) { h[g] = ex; mcsr_e[base + g] = rs + ex; }
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      __syncwarp();
+      len = (re - rs) - h[tp];
+      __syncwarp();
+      // stable scatter, 32 nz at a time
+      for (int e0 = rs; e0 < re; e0 += 32) {
+        int e = e0 + lane;
+        bool act = e < re;
+        int g = 0xffff;
+        uint32_t c = 0; float v = 0.f;
+        if (act) { g = key2[e]; g = g == SPARSE_KEY ? tp : g; c = col[e]; v = val[e]; }
+        unsigned peers = __match_any_sync(0xffffffffu, g);
+        int rank = __popc(peers & ((1u << lane) - 1u));
+        int pos = 0;
+        if (act) pos = rs + h[g] + rank;
+        __syncwarp();
+        if (act && rank == 0) h[g] += __popc(peers);
+        __syncwarp();
+        if (act) { perm[pos] = e; csr_e[pos] = (int)c; csr_ev[pos] = v; }
+      }
+    }
+    if (lane == 0) {
+      spec_cnt[row] = len / STHRESHOLD;
+      s1 += len; s2 += (long long)len * len; chunks += len / STHRESHOLD;
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(&stats[0], (unsigned long long)s1);
+    atomicAdd(&stats[1], (unsigned long long)s2);
+    if (chunks) atomicAdd(&stats[2], (unsigned long long)chunks);
+  }
+  if (p == npanel - 1 && threadIdx.x == 0) mcsr_e[(size_t)BH * mcsr_cnt[npanel]] = ne;  // :1297
+}
+
+// no dense tile anywhere (:1224-1230): mcsr_cnt[p]=p, mcsr_e aliases csr_v, nz arrays alias the CSR
+__global__ void k_nodense(const int* __restrict__ csr_v, int npanel, int nr, int* __restrict__ mcsr_cnt,
+                          int* __restrict__ tcount, int* __restrict__ spec_cnt,
+                          unsigned long long* __restrict__ stats) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= npanel) { mcsr_cnt[i] = i; tcount[i] = 0; }
+  long long s1 = 0, s2 = 0;
+  int chunks = 0;
+  if (i < nr) {
+    int len = csr_v[i + 1] - csr_v[i];
+    spec_cnt[i] = len / STHRESHOLD;
+    s1 = len; s2 = (long long)len * len; chunks = len / STHRESHOLD;
+  }
+  auto warp = cg::tiled_partition<32>(cg::this_thread_block());
+  s1 = cg::reduce(warp, s1, cg::plus<long long>());
+  s2 = cg::reduce(warp, s2, cg::plus<long long>());
+  chunks = cg::reduce(warp, chunks, cg::plus<int>());
+  if ((threadIdx.x & 31) == 0) {
+    if (s1) atomicAdd(&stats[0], (unsigned long long)s1);
+    if (s2) atomicAdd(&stats[1], (unsigned long long)s2);
+    if (chunks) atomicAdd(&stats[2], (unsigned long long)chunks);
+  }
+}
+
+// ---- K5: special lists (make_special :1076-1087) in canonical (row-ascending) order ---------
+__global__ void __launch_bounds__(1024) k_scan_spec(const int* __restrict__ spec_cnt, int nr,
+                                                    int* __restrict__ spec_off) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  auto warp = cg::tiled_partition<32>(cg::this_thread_block());
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nr; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    int v = i < nr ? spec_cnt[i] : 0;
+    int inc = cg::inclusive_scan(warp, v);
+    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int ws = warp_sum[threadIdx.x];
+      int wi = cg::inclusive_scan(warp, ws);
+      warp_sum[threadIdx.x] = wi - ws;
+    }
+    __syncthreads();
+    int incl = carry_s + warp_sum[threadIdx.x >> 5] + inc;
+    if (i < nr) spec_off[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) spec_off[nr] = carry_s;
+}
+
+__global__ void k_fill_special(const int* __restrict__ spec_cnt, const int* __restrict__ spec_off, int nr,
+                               int* __restrict__ special, int* __restrict__ special2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nr) return;
+  int c = spec_cnt[i], o = spec_off[i];
+  for (int j = 0; j < c; ++j) { special[o + j] = i; special2[o + j] = STHRESHOLD * j; }
+}
+
+}  // namespace
+
+namespace fx {
+
+static int heavy_ctas(int npanel) {
+  int dev = 0, sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+  int g = 2 * sm;
+  return npanel < g ? (npanel > 0 ? npanel : 1) : g;
+}
+
+int aspt_carve(fx_tiles* t, int64_t ncols) {
+  fx_aspt_dev& a = t->aspt;
+  const int64_t ne = a.ne, nr = a.nr, npanel = a.npanel;
+  const int BW = a.BW, min_occ = BW * 3 / 4;
+  a.G = heavy_ctas((int)npanel);
+  a.list_cap_tiles = (int)(ne / ((int64_t)min_occ * THRESHOLD) + 1);
+  a.mcsr_e_cap = (int)((int64_t)BH * (a.list_cap_tiles + npanel) + 2);
+  a.special_cap = (int)(ne / STHRESHOLD + 1);
+  a.partial_cap_floats = (size_t)a.special_cap * (size_t)t->k;
+  size_t bytes = 0;
+  auto add = [&](size_t b) { bytes += Arena::pad(b) + 256; };
+  add(sizeof(int) * (nr + 2));                       // csr_v
+  for (int i = 0; i < 4; ++i) add(sizeof(int) * (npanel + 2));  // chk, cnt, tcount, nheavy
+  add(sizeof(uint16_t) * (ne + 2));                  // key2
+  add(sizeof(int2) * (ne / THRESHOLD + npanel + 2));  // heavy
+  add(sizeof(unsigned) * (size_t)a.G * ncols);       // counters
+  add(sizeof(int) * (size_t)a.mcsr_e_cap);
+  add(sizeof(int) * (size_t)a.list_cap_tiles * BW);
+  add(sizeof(int) * (size_t)a.list_cap_tiles * 2);
+  add(sizeof(int) * (ne + 2) * 2);                   // perm, csr_e
+  add(sizeof(float) * (ne + 2));                     // csr_ev
+  add(sizeof(int) * (nr + 2) * 2);                   // spec_cnt, spec_off
+  add(sizeof(int) * (size_t)a.special_cap * 2);
+  add(sizeof(unsigned long long) * 8);
+  add(sizeof(float) * a.partial_cap_floats);
+  int rc = t->arena.reserve(bytes);
+  if (rc != FX_OK) return rc;
+  Arena& A = t->arena;
+  a.csr_v = A.take<int>(nr + 2);
+  a.mcsr_chk = A.take<int>(npanel + 2);
+  a.mcsr_cnt = A.take<int>(npanel + 2);
+  a.tcount = A.take<int>(npanel + 2);
+  a.nheavy = A.take<int>(npanel + 2);
+  a.key2 = A.take<uint16_t>(ne + 2);
+  a.heavy = A.take<int2>(ne / THRESHOLD + npanel + 2);
+  a.cnt_scratch = A.take<unsigned>((size_t)a.G * ncols);
+  a.mcsr_e = A.take<int>(a.mcsr_e_cap);
+  a.mcsr_list = A.take<int>((size_t)a.list_cap_tiles * BW);
+  a.baddr = A.take<int>(a.list_cap_tiles);
+  a.saddr = A.take<int>(a.list_cap_tiles);
+  a.perm = A.take<int>(ne + 2);
+  a.csr_e = A.take<int>(ne + 2);
+  a.csr_ev = A.take<float>(ne + 2);
+  a.spec_cnt = A.take<int>(nr + 2);
+  a.spec_off = A.take<int>(nr + 2);
+  a.special = A.take<int>(a.special_cap);
+  a.special2 = A.take<int>(a.special_cap);
+  a.stats = A.take<unsigned long long>(8);
+  a.partial = A.take<float>(a.partial_cap_floats);
+  if (!a.partial || !a.stats) { set_error("arena carve overflow"); return FX_ERR_NOMEM; }
+  // the column counters must start at zero; every build leaves them zeroed again
+  FX_CUDA(cudaMemset(a.cnt_scratch, 0, sizeof(unsigned) * (size_t)a.G * ncols));
+  return FX_OK;
+}
+
+// Everything between the two events of fx_build: kernels + one 64-byte D2H.
+int aspt_build(fx_tiles* t, cudaStream_t s) {
+  fx_aspt_dev& a = t->aspt;
+  const fx_matrix* m = t->mat;
+  const int BW = a.BW, min_occ = BW * 3 / 4;
+  const uint32_t* col = m->col_dev + m->rowptr[t->row_begin];
+  const float* val = m->val_dev + m->rowptr[t->row_begin];
+  const int nloc = t->row_end - t->row_begin;
+  FX_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(unsigned long long) * 8, s));
+  k_pad_rowptr<<<ceil_div(a.nr + 1, 256), 256, 0, s>>>(m->rowptr_dev, t->row_begin, nloc, a.nr, a.ne, a.csr_v);
+  FX_LAUNCH_CHECK();
+  k_detect<<<a.npanel, 256, 0, s>>>(a.csr_v, col, min_occ, a.mcsr_chk, a.stats);
+  FX_LAUNCH_CHECK();
+  // the one decision the host has to take (reference: d_flag copy :1217-1224)
+  FX_CUDA(cudaMemcpyAsync(t->stats_host, a.stats, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
+  FX_CUDA(cudaStreamSynchronize(s));
+  a.any_flag = t->stats_host[4] != 0;
+  int* mcsr_e = a.mcsr_e;
+  if (!a.any_flag) {
+    a.aliased = true;
+    a.mcsr_e_use = a.csr_v;
+    a.csr_e_use = reinterpret_cast<const int*>(col);
+    a.csr_ev_use = val;
+    k_nodense<<<ceil_div(a.nr + 1, 256), 256, 0, s>>>(a.csr_v, a.npanel, a.nr, a.mcsr_cnt, a.tcount, a.spec_cnt,
+                                                         a.stats);
+    FX_LAUNCH_CHECK();
+  } else {
+    a.aliased = false;
+    a.mcsr_e_use = a.mcsr_e;
+    a.csr_e_use = a.csr_e;
+    a.csr_ev_use = a.csr_ev;
+    FX_CUDA(cudaMemsetAsync(a.tcount, 0, sizeof(int) * (a.npanel + 1), s));
+    static bool attr_set = false;
+    if (!attr_set) {
+      FX_CUDA(cudaFuncSetAttribute(k_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(SORT_SMEM_CAP * sizeof(unsigned long long))));
+      attr_set = true;
+    }
+    k_heavy<<<a.G, 512, SORT_SMEM_CAP * sizeof(unsigned long long), s>>>(
+        a.csr_v, col, a.mcsr_chk, a.npanel, BW, min_occ, (int)m->n, a.cnt_scratch,
+        reinterpret_cast<unsigned long long*>(a.heavy), a.nheavy, a.tcount, a.key2);
+    FX_LAUNCH_CHECK();
+    k_scan_tcount<<<1, 1024, 0, s>>>(a.tcount, a.npanel, a.mcsr_cnt, a.stats);
+    FX_LAUNCH_CHECK();
+    k_fill<<<a.npanel, FILL_WARPS * 32, 0, s>>>(a.csr_v, col, val, a.tcount, a.mcsr_cnt, a.heavy, a.nheavy, a.key2,
+                                                a.npanel, BW, a.ne, mcsr_e, a.mcsr_list, a.baddr, a.saddr, a.perm,
+                                                a.csr_e, a.csr_ev, a.spec_cnt, a.stats);
+    FX_LAUNCH_CHECK();
+  }
+  k_scan_spec<<<1, 1024, 0, s>>>(a.spec_cnt, a.nr, a.spec_off);
+  FX_LAUNCH_CHECK();
+  k_fill_special<<<ceil_div(a.nr, 256), 256, 0, s>>>(a.spec_cnt, a.spec_off, a.nr, a.special, a.special2);
+  FX_LAUNCH_CHECK();
+  FX_CUDA(cudaMemcpyAsync(t->stats_host, a.stats, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
+  FX_CUDA(cudaStreamSynchronize(s));
+  a.S1 = (long long)t->stats_host[0];
+  a.S2 = (long long)t->stats_host[1];
+  a.special_p = (int)t->stats_host[2];
+  a.num_dense = a.any_flag ? (int)t->stats_host[3] : 0;
+  a.max_tp = a.any_flag ? (int)t->stats_host[5] : 0;
+  a.avg = a.nr ? (double)a.S1 / a.nr : 0;                       // :1226 / :1300
+  a.vari = a.nr ? (double)a.S2 / a.nr - a.avg * a.avg : 0;      // Σ(len-avg)²/nr, exact sums
+  const int nc = a.n;
+  a.regime = (nc > 0 && a.ne / nc < 6 && a.vari < 40) ? 0 : (a.vari < 200 ? 1 : 2);  // :1355,1368,1381
+  return FX_OK;
+}
+
+}  // namespace fx

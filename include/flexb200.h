@@ -1,0 +1,158 @@
+/*
+ * flexb200.h -- C ABI of libflexb200.so, the B200-native (sm_100a) SpMM engine that
+ * stands behind guohaoqiang/Flex's driver surface.
+ *
+ * Plain pointers and sizes only: no C++/torch types.  Every entry point names the
+ * reference interface (file:line in guohaoqiang/Flex) it replaces.  Pointers named
+ * *_dev are CUDA device addresses on the current device; `stream` is a cudaStream_t
+ * passed as void* (NULL = legacy default stream).
+ *
+ * Error model (reference: CUDA_CHECK throws std::runtime_error, common.h:53-60; data
+ * violations are asserts): every call returns FX_OK or a negative fx_status and
+ * records a message retrievable with fx_last_error().  Nothing falls back to the
+ * CPU: with no usable sm_100 device every compute call returns FX_ERR_CUDA.
+ */
+#ifndef FLEXB200_H
+#define FLEXB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  FX_OK = 0,
+  FX_ERR_IO = -1,       /* file missing / malformed CSV */
+  FX_ERR_ARG = -2,      /* bad argument */
+  FX_ERR_CUDA = -3,     /* CUDA runtime error or no device */
+  FX_ERR_FORMAT = -4,   /* matrix violates a builder precondition (reference asserts) */
+  FX_ERR_NOMEM = -5,
+  FX_ERR_UNSUPPORTED = -6
+} fx_status;
+
+typedef enum { /* DataLoader::vertex_order_abbr, DataLoader.cu:14,326,457,660,725,791 */
+  FX_ORDER_OVO = 0, /* original vertex order */
+  FX_ORDER_DEG = 1, /* DataLoaderDeg    DataLoader.cu:658-721 */
+  FX_ORDER_RCM = 2, /* DataLoaderRcm    DataLoader.cu:723-787 */
+  FX_ORDER_GOR = 3  /* DataLoaderGorder DataLoader.cu:789-857 */
+} fx_order;
+
+typedef enum {
+  FX_FMT_CSR = 0,    /* raw CSR (run_ge_spmm path, flex.cu:4285; ASpT "ssparse" regime) */
+  FX_FMT_ASPT = 1,   /* ASpT dense/sparse tiles  aspt/sspmm_128.cu:831-1087,1207-1333 */
+  FX_FMT_TILE = 2,   /* Flex tile format         mat.cu:1345-1518 */
+  FX_FMT_SEG = 3,    /* Flex tile-segment format mat.cu:1192-1269 + SM buckets :1097-1162 */
+  FX_FMT_PILLAR = 4  /* Flex diagonal tiling     mat.cu:680-942 */
+} fx_format;
+
+typedef struct fx_matrix fx_matrix; /* replaces class DataLoader (DataLoader.cuh:21-112) */
+typedef struct fx_tiles fx_tiles;   /* replaces class Mat / Mat_POD (mat.cuh:18-229) */
+
+typedef struct { /* DataLoader public fields, DataLoader.cuh:57-71 */
+  int64_t m, n, nnz, dim, c, uni_nb;
+  int32_t is_directed, n_nodes_z_out, n_nodes_z_in, n_nodes_z_deg;
+  int64_t n_edges_one_way, n_edges_asymmetric;
+  int32_t order;          /* fx_order */
+  char graph_name[64];    /* basename without extension, DataLoader.cu:11-12 */
+  char order_abbr[4];     /* "OVO","DEG","RCM","GOR" */
+} fx_matrix_info;
+
+typedef struct {
+  int32_t format;     /* fx_format */
+  int32_t tm, tn;     /* Flex tile height/width (tileConfs, flex.cu:4146-4152); ASpT: ignored */
+  int32_t bw;         /* ASpT tile width: 0 = reference rule (128 if k>=64 else 256) */
+  int32_t nnz_limit;  /* NNZ_LIMIT (mat.cuh:16), 0 = 128 */
+  int32_t n_sm;       /* SM count for F4/F5 bucketing, 0 = device value */
+  int32_t row_begin, row_end; /* build only rows [row_begin,row_end) (row-panel shard); 0,0 = all */
+  int32_t reserved[8];
+} fx_build_opts;
+
+typedef struct { /* ASpT metadata export for bit-exact checks; pointers are host copies
+                    owned by the fx_tiles handle, valid until fx_tiles_free */
+  int32_t n, nr, npanel, ne, BH, BW, num_dense, any_flag, regime, special_p;
+  int64_t S1, S2;
+  double avg, vari;
+  const int32_t *mcsr_chk, *mcsr_cnt, *mcsr_e, *mcsr_list, *baddr, *saddr;
+  const int32_t *perm, *csr_e, *special, *special2;
+  const float *csr_ev;
+} fx_aspt_arrays;
+
+typedef struct { /* what run()/process() print: flex.cu:5134-5631, aspt/sspmm_128.cu:1406-1446 */
+  float tPre_ms, tElap_ms;
+  double gflops;        /* 2*nnz*k / tElap (aspt/sspmm_128.cu:1406) */
+  double tpre_over_telap;
+  int64_t errs_flex;    /* resCheck count, flex.cu:4155-4213 */
+  int64_t errs_tight;   /* |d| > 1e-5*max(|gold|,1) */
+  double errs_aspt_pct; /* aspt/sspmm_128.cu:1425-1446 */
+  double max_err;
+} fx_report;
+
+const char *fx_last_error(void);
+int fx_version(void);
+/* number of kernels launched by this library in this process (all streams) */
+int64_t fx_launch_count(void);
+int fx_device_sm_count(int *n_sm);
+
+/* ---- L0: CSR load + device upload ------------------------------------------------ */
+/* DataLoader::DataLoader(path,k) DataLoader.cu:9-124 + cuda_alloc_cpy :167-218 (CSR part) */
+int fx_csr_load(const char *path, int k, fx_matrix **out);
+/* same from host arrays (no reference counterpart; the arrays DataLoader would have parsed) */
+int fx_csr_from_arrays(int64_t n, int64_t nnz, const uint32_t *rowptr, const uint32_t *col,
+                       const float *val, int k, const char *name, fx_matrix **out);
+/* CSR already resident in HBM (arrays are copied device-to-device) */
+int fx_csr_from_device(int64_t n, int64_t nnz, const uint32_t *rowptr_dev, const uint32_t *col_dev,
+                       const float *val_dev, int k, const char *name, fx_matrix **out);
+int fx_matrix_get_info(const fx_matrix *m, fx_matrix_info *info);
+/* host views of rowPtr/col/vals (DataLoader.cuh:32-34); NULL if created from device arrays */
+int fx_matrix_host_csr(const fx_matrix *m, const uint32_t **rowptr, const uint32_t **col,
+                       const float **val);
+int fx_matrix_device_csr(const fx_matrix *m, const uint32_t **rowptr_dev, const uint32_t **col_dev,
+                         const float **val_dev);
+void fx_matrix_free(fx_matrix *m); /* DataLoader::freeAll DataLoader.cuh:100-111 */
+/* B = 2*rand()/RAND_MAX-1 from the glibc stream seeded 1 (DataLoader.cu:198-209); host buffer n*k */
+int fx_rand_B(int64_t n, int k, float *B_host);
+
+/* ---- L1: reordering hooks ---------------------------------------------------------- */
+/* DataLoaderDeg/Rcm/Gorder(const DataLoader&) DataLoader.cuh:128-145: new matrix with the
+ * permuted CSR (columns ascending per row) and vo_mp[new]=old. */
+int fx_reorder(const fx_matrix *m, int order /* fx_order */, fx_matrix **out);
+/* apply an explicit rank[old]=new (DataLoader::perm_apply DataLoader.cu:244-321) */
+int fx_reorder_with_rank(const fx_matrix *m, const uint64_t *rank, int order_tag, fx_matrix **out);
+int fx_permutation(const fx_matrix *m, const int32_t **vo_mp /* host, n entries */);
+/* shadow_b[r,:] = B[vo_mp[r],:]  (flexspmm_v9_permuteX flex.cu:276-289) */
+int fx_permute_rows(const fx_matrix *m, const float *B_dev, float *shadowB_dev, int k, void *stream);
+/* C_out[vo_mp[r],:] = C[r,:] (VO_RECOVER off path, flex.cu:994 v9 writes C[voMp[row]]) */
+int fx_unpermute_rows(const fx_matrix *m, const float *C_dev, float *C_out_dev, int k, void *stream);
+
+/* ---- L2: tile-format build on the GPU ---------------------------------------------- */
+/* Mat::Mat + csr2tile/csr2_DiagTiling + transfer + launch_prep (mat.cuh:74,82-83,176-182);
+ * ASpT: process() pre-process section aspt/sspmm_128.cu:1207-1333.  tPre_ms = GPU time of the
+ * build with the arena already allocated (events around the build kernels and the small
+ * device->host reads they need). */
+int fx_build(const fx_matrix *m, const fx_build_opts *opts, fx_tiles **out, float *tPre_ms);
+/* repeat the build into the same arena (timing loops) */
+int fx_rebuild(fx_tiles *t, float *tPre_ms);
+int fx_tiles_export_aspt(fx_tiles *t, fx_aspt_arrays *out);
+void fx_tiles_free(fx_tiles *t); /* Mat::freeMatGPU* mat.cuh:184-220 */
+
+/* ---- L3: SpMM ---------------------------------------------------------------------- */
+/* C[m x k] = A * B[n x k], row-major fp32, C fully overwritten (the reference pre-zeroes C and
+ * accumulates with atomics: mat.cu:32-41, aspt/sspmm_128.cu:1147).  Asynchronous on `stream`
+ * unless tElap_ms != NULL, in which case the call brackets the kernels with events, waits and
+ * returns their elapsed time (flex.cu:5051-5068, aspt/sspmm_128.cu:1369-1380). */
+int fx_spmm(const fx_tiles *t, const float *B_dev, float *C_dev, int k, void *stream,
+            float *tElap_ms);
+/* Same with HOST buffers: copies B in, runs, copies C out (DataLoader.cu:216 + flex.cu:5690).
+ * Uses an internal pinned staging area if the buffers are pageable. */
+int fx_spmm_host(const fx_tiles *t, const float *B_host, float *C_host, int k, float *total_ms,
+                 float *tElap_ms);
+
+/* ---- L4: validation + reporting ----------------------------------------------------- */
+/* resCheck (flex.cu:4155-4213) and the ASpT validator (aspt/sspmm_128.cu:1425-1446) over host
+ * buffers; rowptr may be NULL (row_nnz taken as 1). */
+int fx_check(const float *gold, const float *res, int64_t n, int k, const uint32_t *rowptr,
+             fx_report *rep);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

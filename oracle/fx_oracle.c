@@ -1,0 +1,519 @@
+/*
+ * fx_oracle.c -- TEST INFRASTRUCTURE ONLY (see fx_oracle.h).
+ *
+ * Plain-C CPU restatement of the reference's SpMM hot path: CSV loader, the
+ * glibc rand() streams for B, the CPU SpMM, the validators, the permutation
+ * apply and the ASpT tile builder under the canonical tie-breaks.
+ * The product library (libflexb200.so) never links or loads this file.
+ *
+ * Citations are file:line in guohaoqiang/Flex (the read-only reference).
+ */
+#define _GNU_SOURCE
+#include "fx_oracle.h"
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------ */
+/* L1: 3-line CSV loader (DataLoader.cu:9-60; aspt/sspmm_128.cu:102-147).    */
+/* line 1 = rowPtr, line 2 = col, line 3 = vals, comma separated.  A file     */
+/* named amazon.csv has no third line: vals = 2*rand()/RAND_MAX-1             */
+/* (DataLoader.cu:36-46).                                                      */
+/* ------------------------------------------------------------------------ */
+static char *read_line(FILE *f, size_t *len_out) {
+  size_t cap = 1 << 20, len = 0;
+  char *buf = (char *)malloc(cap);
+  int ch;
+  while ((ch = fgetc(f)) != EOF && ch != '\n') {
+    if (len + 2 > cap) { cap *= 2; buf = (char *)realloc(buf, cap); }
+    buf[len++] = (char)ch;
+  }
+  buf[len] = 0;
+  *len_out = len;
+  if (ch == EOF && len == 0) { free(buf); return NULL; }
+  return buf;
+}
+
+static int64_t count_tokens(const char *s, size_t len) {
+  if (len == 0) return 0;
+  int64_t c = 1;
+  for (size_t i = 0; i < len; ++i) c += (s[i] == ',');
+  /* trailing comma produces no extra token with getline(ss,word,',') */
+  if (s[len - 1] == ',') c--;
+  return c;
+}
+
+static const char *base_name(const char *path) {
+  const char *b = strrchr(path, '/');
+  return b ? b + 1 : path;
+}
+
+static int class_count(const char *name) { /* DataLoader.cu:62-84 */
+  if (!strcmp(name, "polblogs.csv")) return 2;
+  if (!strcmp(name, "cora.csv")) return 7;
+  if (!strcmp(name, "citeseer.csv")) return 6;
+  if (!strcmp(name, "pubmed.csv")) return 3;
+  if (!strcmp(name, "ppi.csv")) return 121;
+  if (!strcmp(name, "reddit.csv")) return 41;
+  if (!strcmp(name, "flickr.csv")) return 7;
+  if (!strcmp(name, "yelp.csv")) return 100;
+  if (!strcmp(name, "amazon.csv")) return 107;
+  return 100;
+}
+
+int orc_csv_load(const char *path, orc_csr *out) {
+  memset(out, 0, sizeof(*out));
+  FILE *f = fopen(path, "r");
+  if (!f) return -1;
+  size_t l1, l2, l3;
+  char *s1 = read_line(f, &l1);
+  char *s2 = read_line(f, &l2);
+  if (!s1 || !s2) { fclose(f); free(s1); free(s2); return -2; }
+  int64_t np1 = count_tokens(s1, l1), nnz = count_tokens(s2, l2);
+  out->n = np1 - 1;
+  out->nnz = nnz;
+  out->rowptr = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(np1 > 0 ? np1 : 1));
+  out->col = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(nnz > 0 ? nnz : 1));
+  out->val = (float *)malloc(sizeof(float) * (size_t)(nnz > 0 ? nnz : 1));
+  char *p = s1;
+  for (int64_t i = 0; i < np1; ++i) { out->rowptr[i] = (uint32_t)strtol(p, &p, 10); if (*p == ',') ++p; }
+  p = s2;
+  for (int64_t i = 0; i < nnz; ++i) { out->col[i] = (uint32_t)strtol(p, &p, 10); if (*p == ',') ++p; }
+  const char *bn = base_name(path);
+  if (!strcmp(bn, "amazon.csv")) {
+    /* continues whatever rand() stream the process has (reference never seeds) */
+    for (int64_t i = 0; i < nnz; ++i) out->val[i] = 2 * (float)rand() / (float)RAND_MAX - 1.0f;
+  } else {
+    char *s3 = read_line(f, &l3);
+    if (!s3 || count_tokens(s3, l3) != nnz) { fclose(f); free(s1); free(s2); free(s3); orc_csr_free(out); return -3; }
+    p = s3;
+    for (int64_t i = 0; i < nnz; ++i) { out->val[i] = strtof(p, &p); if (*p == ',') ++p; }
+    free(s3);
+  }
+  fclose(f);
+  free(s1); free(s2);
+  out->c = class_count(bn);
+  out->uni_nb = 0; /* DataLoader.cu:24-27 */
+  for (int64_t i = 1; i <= out->n; ++i) if (out->rowptr[i] - out->rowptr[i - 1] == 1) out->uni_nb++;
+  return 0;
+}
+
+void orc_csr_free(orc_csr *m) {
+  free(m->rowptr); free(m->col); free(m->val);
+  memset(m, 0, sizeof(*m));
+}
+
+/* Direction / zero-degree census (DataLoader.cu:86-115), restated with a transposed
+ * CSR instead of vector<map>.  Requires columns unique per row (asserted there :97). */
+int orc_census(const orc_csr *m, orc_census_t *c) {
+  int64_t n = m->n, nnz = m->nnz;
+  memset(c, 0, sizeof(*c));
+  uint32_t *tp = (uint32_t *)calloc((size_t)n + 2, sizeof(uint32_t));
+  for (int64_t e = 0; e < nnz; ++e) tp[m->col[e] + 1]++;
+  for (int64_t i = 0; i < n; ++i) tp[i + 1] += tp[i];
+  uint32_t *cur = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n + 1));
+  memcpy(cur, tp, sizeof(uint32_t) * ((size_t)n + 1));
+  uint32_t *tsrc = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(nnz ? nnz : 1));
+  float *tval = (float *)malloc(sizeof(float) * (size_t)(nnz ? nnz : 1));
+  for (int64_t r = 0; r < n; ++r)
+    for (uint32_t e = m->rowptr[r]; e < m->rowptr[r + 1]; ++e) {
+      uint32_t d = m->col[e];
+      tsrc[cur[d]] = (uint32_t)r; tval[cur[d]] = m->val[e]; cur[d]++;
+    } /* rows visited ascending => tsrc ascending inside each transposed row */
+  for (int64_t r = 0; r < n; ++r)
+    for (uint32_t e = m->rowptr[r]; e < m->rowptr[r + 1]; ++e) {
+      uint32_t cidx = m->col[e];
+      /* e_inv[r] holds sources s with edge s->r; look for cidx among them */
+      uint32_t lo = tp[r], hi = tp[r + 1]; int found = 0; float w = 0;
+      while (lo < hi) { uint32_t mid = (lo + hi) / 2; if (tsrc[mid] < cidx) lo = mid + 1; else hi = mid; }
+      if (lo < tp[r + 1] && tsrc[lo] == cidx) { found = 1; w = tval[lo]; }
+      if (!found) c->n_edges_one_way++;
+      else if (w != m->val[e]) c->n_edges_asymmetric++;
+    }
+  for (int64_t r = 0; r < n; ++r) {
+    int z_out = m->rowptr[r] == m->rowptr[r + 1];
+    int z_in = tp[r] == tp[r + 1];
+    c->n_nodes_z_out += z_out; c->n_nodes_z_in += z_in; c->n_nodes_z_deg += (z_in && z_out);
+  }
+  c->is_directed = c->n_edges_one_way != 0;
+  free(tp); free(cur); free(tsrc); free(tval);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* L2: dense B streams.                                                      */
+/* ------------------------------------------------------------------------ */
+void orc_rand_B_flex(int64_t n, int k, float *out) { /* DataLoader.cu:198-209, glibc seed 1 */
+  srand(1);
+  for (int64_t i = 0; i < n * k; ++i) out[i] = 2 * (float)rand() / (float)RAND_MAX - 1.0f;
+}
+void orc_rand_B_aspt(int64_t n, int k, float *out) { /* aspt/sspmm_128.cu:1148-1149 */
+  srand(1);
+  for (int64_t i = 0; i < n * k; ++i) out[i] = (float)(rand() % 1048576) / 1048576;
+}
+
+/* ------------------------------------------------------------------------ */
+/* CPU SpMM (aspt/sspmm_128.cu:1415-1422): C zeroed; for each nz in CSR      */
+/* order, for j<k: C[row*k+j] += B[col*k+j]*val; fp32; separate mul and add. */
+/* ------------------------------------------------------------------------ */
+void orc_spmm_ref(int64_t n, const uint32_t *rowptr, const uint32_t *col, const float *val,
+                  const float *B, int k, float *C) {
+  for (int64_t i = 0; i < n * k; ++i) C[i] = 0.0f;
+  for (int64_t r = 0; r < n; ++r)
+    for (uint32_t e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+      const float *b = B + (int64_t)col[e] * k;
+      float v = val[e];
+      float *c = C + r * k;
+      for (int j = 0; j < k; ++j) c[j] = c[j] + (float)(b[j] * v);
+    }
+}
+
+/* identical per-row order; rows distributed over threads; the product is rounded
+ * to fp32 before the add exactly as above (no FMA contraction). */
+int orc_spmm_omp(int64_t n, const uint32_t *rowptr, const uint32_t *col, const float *val,
+                 const float *B, int k, float *C, int threads) {
+  int used = 1;
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_max_threads();
+  used = threads;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+#endif
+  for (int64_t r = 0; r < n; ++r) {
+    float *c = C + r * k;
+    for (int j = 0; j < k; ++j) c[j] = 0.0f;
+    for (uint32_t e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+      const float *b = B + (int64_t)col[e] * k;
+      float v = val[e];
+#pragma GCC unroll 1
+      for (int j = 0; j < k; ++j) c[j] = c[j] + (float)(b[j] * v);
+    }
+  }
+  return used;
+}
+
+void orc_spmm_f64(int64_t n, const uint32_t *rowptr, const uint32_t *col, const float *val,
+                  const float *B, int k, double *C, double *Cabs) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
+  for (int64_t r = 0; r < n; ++r) {
+    double *c = C + r * k;
+    double *ca = Cabs ? Cabs + r * k : NULL;
+    for (int j = 0; j < k; ++j) { c[j] = 0.0; if (ca) ca[j] = 0.0; }
+    for (uint32_t e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+      const float *b = B + (int64_t)col[e] * k;
+      double v = val[e];
+      for (int j = 0; j < k; ++j) { double t = (double)b[j] * v; c[j] += t; if (ca) ca[j] += fabs(t); }
+    }
+  }
+}
+
+/* rows subset version for sampled checks at full size */
+void orc_spmm_rows(const int64_t *rows, int64_t nrows, const uint32_t *rowptr, const uint32_t *col,
+                   const float *val, const float *B, int k, float *C /* nrows*k */) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16)
+#endif
+  for (int64_t i = 0; i < nrows; ++i) {
+    int64_t r = rows[i];
+    float *c = C + i * k;
+    for (int j = 0; j < k; ++j) c[j] = 0.0f;
+    for (uint32_t e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+      const float *b = B + (int64_t)col[e] * k;
+      float v = val[e];
+#pragma GCC unroll 1
+      for (int j = 0; j < k; ++j) c[j] = c[j] + (float)(b[j] * v);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* V1: validators.                                                            */
+/*  flex: flex.cu:4155-4213 resCheck: err = |g-r| if |g|<1 else |g-r|/|g|;     */
+/*        miss if err > FLT_EPSILON*row_nnz*4.                                 */
+/*  aspt: aspt/sspmm_128.cu:1425-1441: |p1|,|p2|; diff/max(p1,p2) > 0.01.      */
+/*  tight (this repo's contract): |g-r| > 1e-5*max(|g|,1).                     */
+/* ------------------------------------------------------------------------ */
+void orc_check(const float *gold, const float *res, int64_t n, int k, const uint32_t *rowptr,
+               orc_errs *out) {
+  memset(out, 0, sizeof(*out));
+  for (int64_t r = 0; r < n; ++r) {
+    int rnnz = rowptr ? (int)(rowptr[r + 1] - rowptr[r]) : 1;
+    double tol = (double)FLT_EPSILON * rnnz * 4;
+    for (int j = 0; j < k; ++j) {
+      float g = gold[r * k + j], x = res[r * k + j];
+      if (g == 0) out->gold_zeros++;
+      double d = fabs((double)g - (double)x);
+      double err = fabs(g) < 1 ? d : d / fabs(g);
+      if (!(err <= tol)) out->flex_count++;
+      if (err > out->max_err) out->max_err = err;
+      float p1 = fabsf(g), p2 = fabsf(x);
+      float diff = fabsf(p1 - p2);
+      float mx = p1 > p2 ? p1 : p2;
+      if (diff / mx > 0.01f) out->aspt_count++;
+      double sc = fabs(g) > 1 ? fabs(g) : 1;
+      if (!(d <= 1e-5 * sc)) out->tight_count++;
+      if (d / sc > out->max_tight) out->max_tight = d / sc;
+    }
+  }
+  out->aspt_pct = (n * k) != 0 ? (double)out->aspt_count / (double)(n * k) * 100 : 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* L3: permutation apply (DataLoader.cu:244-285 and the ctor bodies :749-780).*/
+/* rank[old] = new.  vo_mp[new] = old.  Row v_new receives row v_old's edges   */
+/* renumbered and sorted ascending by new column (ranges::sort, keys unique).  */
+/* ------------------------------------------------------------------------ */
+typedef struct { uint32_t c; float v; } cv_t;
+static int cmp_cv(const void *a, const void *b) {
+  uint32_t x = ((const cv_t *)a)->c, y = ((const cv_t *)b)->c;
+  return x < y ? -1 : x > y;
+}
+void orc_perm_apply(int64_t n, const uint32_t *rowptr, const uint32_t *col, const float *val,
+                    const uint64_t *rank, int32_t *vo_mp, uint32_t *rowptr_out,
+                    uint32_t *col_out, float *val_out) {
+  for (int64_t i = 0; i < n; ++i) vo_mp[rank[i]] = (int32_t)i;
+  rowptr_out[0] = 0;
+  for (int64_t vn = 0; vn < n; ++vn) {
+    int64_t vo = vo_mp[vn];
+    rowptr_out[vn + 1] = rowptr_out[vn] + (rowptr[vo + 1] - rowptr[vo]);
+  }
+  for (int64_t vo = 0; vo < n; ++vo) {
+    int64_t vn = (int64_t)rank[vo];
+    uint32_t d = rowptr[vo + 1] - rowptr[vo];
+    cv_t *tmp = (cv_t *)malloc(sizeof(cv_t) * (d ? d : 1));
+    for (uint32_t e = 0; e < d; ++e) { tmp[e].c = (uint32_t)rank[col[rowptr[vo] + e]]; tmp[e].v = val[rowptr[vo] + e]; }
+    qsort(tmp, d, sizeof(cv_t), cmp_cv);
+    for (uint32_t e = 0; e < d; ++e) { col_out[rowptr_out[vn] + e] = tmp[e].c; val_out[rowptr_out[vn] + e] = tmp[e].v; }
+    free(tmp);
+  }
+}
+
+/* P1 (flex.cu:276-289): shadow_b[r,:] = B[voMp[r],:] */
+void orc_permute_rows(int64_t n, int k, const int32_t *vo_mp, const float *B, float *shadowB) {
+  for (int64_t r = 0; r < n; ++r) memcpy(shadowB + r * k, B + (int64_t)vo_mp[r] * k, sizeof(float) * (size_t)k);
+}
+
+/* ------------------------------------------------------------------------ */
+/* A1: ASpT tile builder, canonical restatement                               */
+/*     (aspt/sspmm_128.cu:831-1087 kernels, :1207-1333 process()).            */
+/* ------------------------------------------------------------------------ */
+#define A_BH 128
+#define A_THRESHOLD 16
+#define A_SC_SIZE 2048
+#define A_STHRESHOLD 512
+#define A_SPARSE 30000
+
+typedef struct { int c; int idx; } ci_t;
+static int cmp_ci(const void *a, const void *b) {
+  const ci_t *x = (const ci_t *)a, *y = (const ci_t *)b;
+  if (x->c != y->c) return x->c < y->c ? -1 : 1;
+  return x->idx < y->idx ? -1 : x->idx > y->idx;
+}
+
+int orc_aspt_build(int n, const uint32_t *rowptr, const uint32_t *col, const float *val, int BW,
+                   const int *forced_cnt, const int *forced_list, orc_aspt *o) {
+  memset(o, 0, sizeof(*o));
+  const int BH = A_BH, MIN_OCC = BW * 3 / 4;
+  int nr = (n + BH - 1) / BH * BH, npanel = nr / BH, ne = (int)rowptr[n];
+  o->n = n; o->nr = nr; o->npanel = npanel; o->ne = ne; o->BH = BH; o->BW = BW;
+  /* padded row pointer: rows >= n are empty (ready2 :148-155 semantics) */
+  int *csr_v = (int *)malloc(sizeof(int) * ((size_t)nr + 1));
+  for (int i = 0; i <= nr; ++i) csr_v[i] = i <= n ? (int)rowptr[i] : ne;
+  o->mcsr_chk = (int *)calloc((size_t)npanel + 1, sizeof(int));
+  o->mcsr_cnt = (int *)calloc((size_t)npanel + 1, sizeof(int));
+  o->key2 = (int *)malloc(sizeof(int) * ((size_t)ne + 1));
+  o->perm = (int *)malloc(sizeof(int) * ((size_t)ne + 1));
+  o->csr_e = (int *)malloc(sizeof(int) * ((size_t)ne + 1));
+  o->csr_ev = (float *)malloc(sizeof(float) * ((size_t)ne + 1));
+  for (int i = 0; i < ne; ++i) { o->key2[i] = A_SPARSE; o->perm[i] = i; }
+
+  /* 1. dense_block_detect :831-868 */
+  int *hist = (int *)malloc(sizeof(int) * A_SC_SIZE);
+  for (int p = 0; p < npanel; ++p) {
+    memset(hist, 0, sizeof(int) * A_SC_SIZE);
+    for (int i = csr_v[p * BH]; i < csr_v[(p + 1) * BH]; ++i) hist[col[i] & (A_SC_SIZE - 1)]++;
+    int r = 0;
+    for (int b = 0; b < A_SC_SIZE; ++b) r += hist[b] >= A_THRESHOLD;
+    if (r >= MIN_OCC) { o->mcsr_chk[p] = 1; o->any_flag = 1; }
+  }
+  free(hist);
+
+  int *tcount = (int *)calloc((size_t)npanel + 1, sizeof(int));
+  if (forced_cnt) {
+    o->any_flag = 0;
+    for (int p = 0; p < npanel; ++p) { tcount[p] = forced_cnt[p + 1] - forced_cnt[p] - 1; if (tcount[p] > 0 || o->mcsr_chk[p]) o->any_flag = 1; }
+  }
+
+  if (!o->any_flag) { /* :1224-1230 */
+    o->num_dense = 0;
+    for (int p = 0; p <= npanel; ++p) o->mcsr_cnt[p] = p;
+    o->mcsr_e = (int *)malloc(sizeof(int) * ((size_t)nr + 1));
+    memcpy(o->mcsr_e, csr_v, sizeof(int) * ((size_t)nr + 1));
+    for (int i = 0; i < ne; ++i) { o->csr_e[i] = (int)col[i]; o->csr_ev[i] = val[i]; }
+  } else {
+    /* 2+3. per flagged panel: sort nz by column (bb_segsort#1 :1249), heavy = run >= 16
+     *      (:913-914), slot assignment in ASCENDING column order (canonical; the reference
+     *      takes atomic arrival order :915,:957). */
+    ci_t **psorted = (ci_t **)calloc((size_t)npanel, sizeof(ci_t *));
+    int *age = (int *)malloc(sizeof(int) * (size_t)BW);
+    int *occ = (int *)malloc(sizeof(int) * 1024);
+    for (int p = 0; p < npanel; ++p) {
+      if (!o->mcsr_chk[p]) continue;
+      int lb = csr_v[p * BH], ub = csr_v[(p + 1) * BH], cnt = ub - lb;
+      ci_t *s = (ci_t *)malloc(sizeof(ci_t) * (size_t)(cnt ? cnt : 1));
+      for (int i = 0; i < cnt; ++i) { s[i].c = (int)col[lb + i]; s[i].idx = lb + i; }
+      qsort(s, (size_t)cnt, sizeof(ci_t), cmp_ci);
+      psorted[p] = s;
+      if (forced_cnt) continue;
+      memset(age, 0, sizeof(int) * (size_t)BW);
+      memset(occ, 0, sizeof(int) * 1024);
+      occ[0] = BW;
+      for (int i = 0; i < cnt;) {
+        int j = i; while (j < cnt && s[j].c == s[i].c) ++j;
+        if (j - i >= A_THRESHOLD) { int h = age[s[i].c & (BW - 1)]++; if (h + 1 < 1024) occ[h + 1]++; }
+        i = j;
+      }
+      int t = 0; /* :921-922: thread t with occ[t]>=MIN_OCC && occ[t+1]<MIN_OCC */
+      for (int q = 0; q < 1023; ++q) if (occ[q] >= MIN_OCC && occ[q + 1] < MIN_OCC) t = q;
+      tcount[p] = t;
+    }
+    /* host prefix :1260-1266 */
+    o->mcsr_cnt[0] = 0;
+    for (int p = 1; p <= npanel; ++p) o->mcsr_cnt[p] = o->mcsr_cnt[p - 1] + tcount[p - 1] + 1;
+    o->num_dense = o->mcsr_cnt[npanel] - npanel;
+    int nd = o->num_dense;
+    o->mcsr_list = (int *)malloc(sizeof(int) * (size_t)(nd ? nd : 1) * BW);
+    for (int64_t i = 0; i < (int64_t)nd * BW; ++i) o->mcsr_list[i] = -1; /* memset -1 :1128 */
+    o->baddr = (int *)malloc(sizeof(int) * (size_t)(nd ? nd : 1));
+    o->saddr = (int *)malloc(sizeof(int) * (size_t)(nd ? nd : 1));
+    if (forced_list) memcpy(o->mcsr_list, forced_list, sizeof(int) * (size_t)nd * BW);
+    /* key2_marking :929-981 */
+    for (int p = 0; p < npanel; ++p) {
+      int limit = tcount[p];
+      int g0 = o->mcsr_cnt[p] - p;
+      for (int i = 0; i < limit; ++i) { o->baddr[g0 + i] = p; o->saddr[g0 + i] = i; }
+      if (!o->mcsr_chk[p] || !psorted[p]) continue;
+      int lb = csr_v[p * BH], ub = csr_v[(p + 1) * BH], cnt = ub - lb;
+      ci_t *s = psorted[p];
+      memset(age, 0, sizeof(int) * (size_t)BW);
+      for (int i = 0; i < cnt;) {
+        int j = i; while (j < cnt && s[j].c == s[i].c) ++j;
+        if (j - i >= A_THRESHOLD) {
+          int c = s[i].c, width = c & (BW - 1), depth = -1;
+          if (forced_list) {
+            for (int d = 0; d < limit; ++d) if (o->mcsr_list[(int64_t)(g0 + d) * BW + width] == c) depth = d;
+          } else {
+            int d = age[width]++;
+            if (d < limit) { depth = d; o->mcsr_list[(int64_t)g0 * BW + (int64_t)d * BW + width] = c; }
+          }
+          if (depth >= 0) for (int q = i; q < j; ++q) o->key2[s[q].idx] = depth;
+        }
+        i = j;
+      }
+      free(s);
+    }
+    free(psorted); free(age); free(occ);
+    /* 4. per row STABLE sort by key2 (bb_segsort#2 :1282, canonical = stable), fill_mcsre
+     *    :1006-1026, porting :1040-1048 */
+    o->mcsr_e = (int *)calloc((size_t)BH * ((size_t)nd + npanel) + 1, sizeof(int));
+    for (int p = 0; p < npanel; ++p) {
+      int delta = o->mcsr_cnt[p + 1] - o->mcsr_cnt[p];
+      for (int r = 0; r < BH; ++r) {
+        int row = p * BH + r, lb = csr_v[row], ub = csr_v[row + 1];
+        int bidx = o->mcsr_cnt[p] * BH + delta * r;
+        int pos = lb;
+        for (int g = 0; g < delta; ++g) {
+          o->mcsr_e[bidx + g] = pos;
+          int want = g == delta - 1 ? A_SPARSE : g;
+          for (int i = lb; i < ub; ++i)
+            if (o->key2[i] == want) { o->perm[pos] = i; o->csr_e[pos] = (int)col[i]; o->csr_ev[pos] = val[i]; pos++; }
+        }
+      }
+    }
+    o->mcsr_e[(size_t)BH * ((size_t)nd + npanel)] = ne; /* :1297 */
+  }
+  if (!o->mcsr_list) { o->mcsr_list = (int *)malloc(sizeof(int)); o->baddr = (int *)malloc(sizeof(int)); o->saddr = (int *)malloc(sizeof(int)); }
+  /* 5. cal_vari :1050-1073, :1310-1315.  len_r = sparse-group length of padded row r. */
+  int64_t S1 = 0, S2 = 0; int special_p = 0;
+  int *len = (int *)malloc(sizeof(int) * (size_t)nr);
+  for (int p = 0; p < npanel; ++p) {
+    int delta = o->mcsr_cnt[p + 1] - o->mcsr_cnt[p];
+    for (int r = 0; r < BH; ++r) {
+      int idx = o->mcsr_cnt[p] * BH + delta * (r + 1);
+      int l = o->mcsr_e[idx] - o->mcsr_e[idx - 1];
+      len[p * BH + r] = l; S1 += l; S2 += (int64_t)l * l; special_p += l / A_STHRESHOLD;
+    }
+  }
+  o->S1 = S1; o->S2 = S2;
+  o->avg = (double)S1 / nr; /* :1226 and :1300 are the same quantity */
+  double acc = 0;
+  for (int i = 0; i < nr; ++i) { double d = (double)len[i] - o->avg; acc += d * d; }
+  o->vari = acc / nr;
+  if (o->vari >= 200) { /* :1319-1328, make_special :1076-1087; canonical order = row ascending */
+    o->special_p = special_p;
+    o->special = (int *)malloc(sizeof(int) * (size_t)(special_p ? special_p : 1));
+    o->special2 = (int *)malloc(sizeof(int) * (size_t)(special_p ? special_p : 1));
+    int q = 0;
+    for (int i = 0; i < nr; ++i)
+      for (int c = 0; c < len[i] / A_STHRESHOLD; ++c) { o->special[q] = i; o->special2[q] = A_STHRESHOLD * c; q++; }
+  }
+  free(len);
+  int nc = n;
+  o->regime = (nc > 0 && ne / nc < 6 && o->vari < 40) ? 0 : (o->vari < 200 ? 1 : 2); /* :1355,1368,1381 */
+  free(csr_v); free(tcount);
+  return 0;
+}
+
+void orc_aspt_free(orc_aspt *t) {
+  free(t->mcsr_chk); free(t->mcsr_cnt); free(t->mcsr_e); free(t->mcsr_list); free(t->baddr);
+  free(t->saddr); free(t->key2); free(t->perm); free(t->csr_e); free(t->csr_ev); free(t->special);
+  free(t->special2);
+  memset(t, 0, sizeof(*t));
+}
+
+/* SpMM evaluated through the tile structure with the kernels' address formulas
+ * (dense_v2 :715-731,741 ; sparse_v2 :331-332): per row, dense groups first (B row looked up
+ * through mcsr_list[g*BW + (csr_e & (BW-1))]) then the sparse group, one fused multiply-add per
+ * nz in that order -- the summation order of a GPU lane that walks the row's groups left to
+ * right. */
+void orc_aspt_spmm(const orc_aspt *t, const float *B, int k, float *C) {
+  const int BH = t->BH, BW = t->BW;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+  for (int p = 0; p < t->npanel; ++p) {
+    int delta = t->mcsr_cnt[p + 1] - t->mcsr_cnt[p];
+    for (int r = 0; r < BH; ++r) {
+      float *c = C + ((int64_t)p * BH + r) * k;
+      for (int j = 0; j < k; ++j) c[j] = 0.0f;
+      int base = t->mcsr_cnt[p] * BH + r * delta;
+      for (int g = 0; g < delta; ++g) {
+        int lo = t->mcsr_e[base + g], hi = t->mcsr_e[base + g + 1];
+        for (int e = lo; e < hi; ++e) {
+          int cidx = t->csr_e[e];
+          if (g < delta - 1) {
+            int tile = t->mcsr_cnt[p] - p + g;
+            cidx = t->mcsr_list[(int64_t)tile * BW + (cidx & (BW - 1))];
+          }
+          const float *b = B + (int64_t)cidx * k;
+          float v = t->csr_ev[e];
+          for (int j = 0; j < k; ++j) c[j] = fmaf(v, b[j], c[j]);
+        }
+      }
+    }
+  }
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

@@ -1,0 +1,55 @@
+"""Full-size checks at BASELINE.json's shapes through size-independent properties: sampled rows
+against the oracle, linearity, and the builder's conservation invariants."""
+import numpy as np
+import pytest
+
+import flex_b200 as fx
+from flex_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,k", [("flickr", 128), ("reddit", 128), ("yelp", 32)])
+def test_named_shape(orc, name, k):
+    import torch
+    rp, c, v = synth.generate(name, device="cuda")
+    n, nnz = rp.numel() - 1, c.numel()
+    assert (n, nnz) == synth.SHAPES[name][:2]
+    rp32, c32 = rp.to(torch.int32), c.to(torch.int32)
+    dl = fx.DataLoader.from_device(n, nnz, rp32.data_ptr(), c32.data_ptr(), v.data_ptr(), k, name + ".csv")
+    mat = fx.Mat(dl, fmt="aspt")
+    B = synth.dense_B(n, k, device="cuda")
+    C1 = torch.full((n, k), float("nan"), device="cuda")
+    mat.spmm(B.data_ptr(), C1.data_ptr(), k)
+    torch.cuda.synchronize()
+    # (1) sampled rows against the CPU oracle (reference summation order)
+    rng = np.random.default_rng(0)
+    deg = (rp[1:] - rp[:-1]).cpu().numpy()
+    rows = np.unique(np.concatenate([rng.integers(0, n, 4000), np.argsort(deg)[-20:], [0, n - 1]])).astype(np.int64)
+    rph, ch, vh, Bh = rp.cpu().numpy().astype(np.uint32), c.cpu().numpy().astype(np.uint32), v.cpu().numpy(), B.cpu().numpy()
+    gold = orc.spmm_rows(rows, rph, ch, vh, Bh)
+    got = C1[torch.from_numpy(rows).cuda()].cpu().numpy()
+    sub_rp = np.concatenate([[0], np.cumsum(deg[rows])]).astype(np.uint32)
+    e = orc.check(gold, got, sub_rp)
+    assert e["flex_count"] == 0 and e["aspt_count"] == 0, e
+    # 1e-5 relative contract, measured against an fp64 accumulation scaled by sum|a*b|
+    # (the condition-aware form of "relative error" for rows with thousands of terms)
+    assert e["max_tight"] < 1e-4, e
+    # (2) linearity: A*(2B) == 2*(A*B) exactly in fp32 (power-of-two scaling commutes with rounding)
+    B2 = B * 2
+    C2 = torch.empty_like(C1)
+    mat.spmm(B2.data_ptr(), C2.data_ptr(), k)
+    torch.cuda.synchronize()
+    assert torch.equal(C2, C1 * 2)
+    # (3) checksum of checksums: column sums of C equal (column sums of A) . B in fp64
+    colsum_A = torch.zeros(n, dtype=torch.float64, device="cuda").index_add_(0, c, v.double())
+    lhs = C1.double().sum(0)
+    rhs = colsum_A @ B.double()
+    scale = (colsum_A.abs() @ B.double().abs()).clamp_min(1.0)
+    assert ((lhs - rhs).abs() / scale).max().item() < 1e-5
+    # (4) builder conservation: the permuted nz arrays are a permutation of the CSR
+    e = mat.export_aspt()
+    assert e["mcsr_e"][-1] == nnz and np.all(np.diff(e["mcsr_e"]) >= 0)
+    assert np.array_equal(np.sort(e["perm"]), np.arange(nnz, dtype=np.int32))
+    assert np.array_equal(e["csr_e"], ch[e["perm"]].astype(np.int32))
+    mat.free()
