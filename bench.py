@@ -143,13 +143,17 @@ def cpu_baseline(rp, c, v, Bh, k, budget_s=12.0):
     rows = max(1, min(n, rows))
     sub = rp[:rows + 1].copy()
     out = np.empty((rows, k), np.float32)
-    t0 = time.perf_counter()
-    orc.spmm_omp(sub, c[:sub[-1]], v[:sub[-1]], Bh, out=out)
-    dt = time.perf_counter() - t0
     nnz_s = int(sub[-1])
-    return {"value": 2.0 * nnz_s * k / dt / 1e9, "unit": "GFLOP/s", "cores": int(cores), "kind": "port",
+    passes, t0 = 0, time.perf_counter()
+    while True:
+        orc.spmm_omp(sub, c[:nnz_s], v[:nnz_s], Bh, out=out)
+        passes += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or passes >= 1000:
+            break
+    return {"value": 2.0 * nnz_s * k * passes / dt / 1e9, "unit": "GFLOP/s", "cores": int(cores), "kind": "port",
             "sample": f"rows [0,{rows}) of the workload ({nnz_s} nz, {100.0 * nnz_s / int(rp[-1]):.1f}% of nnz), "
-                      f"1 pass, {dt:.2f} s, OpenMP row-parallel restatement of aspt/sspmm_128.cu:1415-1422"}
+                      f"{passes} passes, {dt:.2f} s, OpenMP row-parallel restatement of aspt/sspmm_128.cu:1415-1422"}
 
 
 def run_reference(args, k):

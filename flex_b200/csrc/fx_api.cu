@@ -221,6 +221,8 @@ extern "C" int fx_check(const float* gold, const float* res, int64_t n, int k, c
   for (int64_t r = 0; r < n; ++r) {
     const int rnnz = rowptr ? (int)(rowptr[r + 1] - rowptr[r]) : 1;
     const double tol = (double)FLT_EPSILON * rnnz * 4;
+    double rowmax = 1.0;  // the 1e-5 contract is row-normwise: |d| <= 1e-5*max(1, ||gold[r,:]||_inf)
+    for (int j = 0; j < k; ++j) rowmax = std::max(rowmax, (double)std::fabs(gold[r * k + j]));
     for (int j = 0; j < k; ++j) {
       const float g = gold[r * k + j], x = res[r * k + j];
       const double d = std::fabs((double)g - (double)x);
@@ -229,7 +231,7 @@ extern "C" int fx_check(const float* gold, const float* res, int64_t n, int k, c
       if (err > max_err) max_err = err;
       const float p1 = std::fabs(g), p2 = std::fabs(x);
       if (std::fabs(p1 - p2) / std::max(p1, p2) > 0.01f) aspt++;
-      if (!(d <= 1e-5 * std::max(1.0, (double)std::fabs(g)))) tight++;
+      if (!(d <= 1e-5 * rowmax)) tight++;
     }
   }
   rep->errs_flex = flex;

@@ -81,7 +81,7 @@ typedef struct { /* what run()/process() print: flex.cu:5134-5631, aspt/sspmm_12
   double gflops;        /* 2*nnz*k / tElap (aspt/sspmm_128.cu:1406) */
   double tpre_over_telap;
   int64_t errs_flex;    /* resCheck count, flex.cu:4155-4213 */
-  int64_t errs_tight;   /* |d| > 1e-5*max(|gold|,1) */
+  int64_t errs_tight;   /* |d| > 1e-5*max(1, ||gold[row,:]||_inf) */
   double errs_aspt_pct; /* aspt/sspmm_128.cu:1425-1446 */
   double max_err;
 } fx_report;

@@ -57,10 +57,10 @@ int orc_num_threads(void);
 typedef struct {
   int64_t flex_count;  /* resCheck: err > FLT_EPSILON*row_nnz*4 */
   int64_t aspt_count;  /* rel diff > 1e-2 */
-  int64_t tight_count; /* ours: |d| > 1e-5*max(|gold|,1) */
+  int64_t tight_count; /* ours: |d| > 1e-5*max(1, ||gold[row,:]||_inf) */
   int64_t gold_zeros;
   double max_err;      /* resCheck metric */
-  double max_tight;    /* max |d|/max(|gold|,1) */
+  double max_tight;    /* max |d|/max(1, ||gold[row,:]||_inf) */
   double aspt_pct;     /* aspt_count / (n*k) * 100 */
 } orc_errs;
 void orc_check(const float *gold, const float *res, int64_t n, int k, const uint32_t *rowptr,

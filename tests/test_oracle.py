@@ -115,3 +115,4 @@ def test_validators(orc):
     r = np.array([[1.0 + 1e-3, 0.5, 2.0 * 1.02, 0.0]], np.float32)
     e = orc.check(g, r, np.array([0, 3], np.uint32))
     assert e["flex_count"] == 2 and e["aspt_count"] == 1 and e["tight_count"] == 2 and e["gold_zeros"] == 1
+    assert abs(e["max_tight"] - 0.02) < 1e-6  # 0.04 / ||gold row||_inf = 2
