@@ -201,6 +201,39 @@ __global__ void __launch_bounds__(1024) k_scan_tcount(const int* __restrict__ tc
   if (threadIdx.x == 0) { stats[3] = (unsigned long long)(carry_s - npanel); stats[5] = (unsigned long long)maxtp; }
 }
 
+// ordered compaction of the panel ids into "has dense tiles" / "has none" (SpMM launches one grid each)
+__global__ void __launch_bounds__(1024) k_panel_lists(const int* __restrict__ tcount, int npanel,
+                                                      int* __restrict__ plain, int* __restrict__ tiled,
+                                                      unsigned long long* __restrict__ stats) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  auto warp = cg::tiled_partition<32>(cg::this_thread_block());
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < npanel; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    int f = i < npanel ? (tcount[i] > 0) : 0;
+    int inc = cg::inclusive_scan(warp, f);
+    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int ws = warp_sum[threadIdx.x];
+      int wi = cg::inclusive_scan(warp, ws);
+      warp_sum[threadIdx.x] = wi - ws;
+    }
+    __syncthreads();
+    int incl = carry_s + warp_sum[threadIdx.x >> 5] + inc;  // tiled panels among [0, i]
+    if (i < npanel) {
+      if (f) tiled[incl - 1] = i;
+      else plain[i - incl] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) stats[6] = (unsigned long long)carry_s;
+}
+
 // ---- K4: slot lists, per-row group offsets, stable partition of the nz ---------------------
 // (key2_marking's list writes :958-959,946-949; bb_segsort#2 :1282; fill_mcsre :1006-1038;
 //  porting :1040-1048; the length statistics of cal_vari :1050-1073)
@@ -382,7 +415,7 @@ int aspt_carve(fx_tiles* t, int64_t ncols) {
   size_t bytes = 0;
   auto add = [&](size_t b) { bytes += Arena::pad(b) + 256; };
   add(sizeof(int) * (nr + 2));                       // csr_v
-  for (int i = 0; i < 4; ++i) add(sizeof(int) * (npanel + 2));  // chk, cnt, tcount, nheavy
+  for (int i = 0; i < 6; ++i) add(sizeof(int) * (npanel + 2));  // chk, cnt, tcount, nheavy, 2 panel lists
   add(sizeof(uint16_t) * (ne + 2));                  // key2
   add(sizeof(int2) * (ne / THRESHOLD + npanel + 2));  // heavy
   add(sizeof(unsigned) * (size_t)a.G * ncols);       // counters
@@ -403,6 +436,8 @@ int aspt_carve(fx_tiles* t, int64_t ncols) {
   a.mcsr_cnt = A.take<int>(npanel + 2);
   a.tcount = A.take<int>(npanel + 2);
   a.nheavy = A.take<int>(npanel + 2);
+  a.plist_plain = A.take<int>(npanel + 2);
+  a.plist_tiled = A.take<int>(npanel + 2);
   a.key2 = A.take<uint16_t>(ne + 2);
   a.heavy = A.take<int2>(ne / THRESHOLD + npanel + 2);
   a.cnt_scratch = A.take<unsigned>((size_t)a.G * ncols);
@@ -469,6 +504,8 @@ int aspt_build(fx_tiles* t, cudaStream_t s) {
     FX_LAUNCH_CHECK();
     k_scan_tcount<<<1, 1024, 0, s>>>(a.tcount, a.npanel, a.mcsr_cnt, a.stats);
     FX_LAUNCH_CHECK();
+    k_panel_lists<<<1, 1024, 0, s>>>(a.tcount, a.npanel, a.plist_plain, a.plist_tiled, a.stats);
+    FX_LAUNCH_CHECK();
     k_fill<<<a.npanel, FILL_WARPS * 32, 0, s>>>(a.csr_v, col, val, a.tcount, a.mcsr_cnt, a.heavy, a.nheavy, a.key2,
                                                 a.npanel, BW, a.ne, mcsr_e, a.mcsr_list, a.baddr, a.saddr, a.perm,
                                                 a.csr_e, a.csr_ev, a.spec_cnt, a.stats);
@@ -485,6 +522,8 @@ int aspt_build(fx_tiles* t, cudaStream_t s) {
   a.special_p = (int)t->stats_host[2];
   a.num_dense = a.any_flag ? (int)t->stats_host[3] : 0;
   a.max_tp = a.any_flag ? (int)t->stats_host[5] : 0;
+  a.n_tiled = a.any_flag ? (int)t->stats_host[6] : 0;
+  a.n_plain = a.npanel - a.n_tiled;
   a.avg = a.nr ? (double)a.S1 / a.nr : 0;                       // :1226 / :1300
   a.vari = a.nr ? (double)a.S2 / a.nr - a.avg * a.avg : 0;      // Σ(len-avg)²/nr, exact sums
   const int nc = a.n;

@@ -109,6 +109,8 @@ struct fx_aspt_dev {  // device-side ASpT format (aspt/sspmm_128.cu:76-90 global
   unsigned* cnt_scratch = nullptr;  // G x ncols saturating per-column counters (kept zeroed)
   int G = 0;
   int *spec_cnt = nullptr, *spec_off = nullptr, *special = nullptr, *special2 = nullptr;
+  int *plist_plain = nullptr, *plist_tiled = nullptr;  // panels without / with dense tiles (ascending)
+  int n_plain = 0, n_tiled = 0;
   unsigned long long* stats = nullptr;  // [0]=S1 [1]=S2 [2]=special chunks [3]=num_dense [4]=any flag
   float* partial = nullptr;             // special_p_cap x k partial sums of 512-chunks
   size_t partial_cap_floats = 0;

@@ -51,8 +51,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+// acc += v * b with two packed FFMA2 (fma.rn.f32x2, sm_100+): same rounding as four fmaf, half the
+// issue slots -- the panel kernel is issue-bound, not FMA-bound.
 __device__ __forceinline__ void fma4(float4& a, float v, const float4& b) {
-  a.x = fmaf(v, b.x, a.x); a.y = fmaf(v, b.y, a.y); a.z = fmaf(v, b.z, a.z); a.w = fmaf(v, b.w, a.w);
+  unsigned long long vv, b01, b23, a01, a23;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(vv) : "f"(v));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b01) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b23) : "f"(b.z), "f"(b.w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a01) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a23) : "f"(a.z), "f"(a.w));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a01) : "l"(vv), "l"(b01));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a23) : "l"(vv), "l"(b23));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(a01));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.z), "=f"(a.w) : "l"(a23));
 }
 
 // acc += sum over nz [lo,hi) of val * B[col,:]  with B read from global memory (L1/L2 path).
@@ -114,117 +125,243 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special(PanelArgs a, 
   const int row = special[item], off = special2[item];
   const int p = row / BH, r = row % BH;
   const int cnt0 = a.mcsr_cnt[p], delta = a.mcsr_cnt[p + 1] - cnt0;
-  const int lo = a.mcsr_e[cnt0 * BH + (r + 1) * delta - 1] + off;
+  // the row's nch chunks are its LAST nch*512 nz (the panel kernel streams everything before them)
+  const int nch = a.spec_off[row + 1] - a.spec_off[row];
+  const int lo = a.mcsr_e[cnt0 * BH + (r + 1) * delta] - nch * STHRESHOLD + off;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   accum_global<LPR>(tile, lo, lo + STHRESHOLD, a.csr_e, a.csr_ev, reinterpret_cast<const float4*>(a.B) + c4, k4, acc);
   if (col_ok) reinterpret_cast<float4*>(partial)[(size_t)item * k4 + c4] = acc;
 }
 
-// ---- panel kernel: one CTA per 128-row panel -------------------------------------------------
-template <int KC>
-__global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_panel(PanelArgs a) {
-  constexpr int LPR = KC / 4, RPW = 32 / LPR;
+// ---- panel kernel: one CTA per 128-row panel, nz-balanced inside the CTA ----------------------
+// The panel's handled nz (every row's [dense groups | sparse tail], i.e. everything except the
+// 512-chunks k_spmm_special takes from the END of long sparse groups) form one logical stream of
+// T nz.  The CTA's NW workers (a worker = LPR lanes = one row of C at a time) each take T/NW
+// consecutive nz of that stream, whatever rows they fall in: no warp idles behind a long row and
+// every worker issues long runs of independent 128-bit B loads.  Rows are looked up through a
+// 129-entry prefix table in shared memory.  A row that lies inside one worker's range is stored
+// directly; the (at most two) rows a worker shares with its neighbours are reduced through a
+// shared-memory slot in worker order, so every C element is still written once, deterministically.
+// TILES=false: panels without a dense tile -- no dynamic shared memory, the SM keeps its L1.
+// TILES=true : the first TS dense tiles of the panel are TMA-staged in shared memory; nz of those
+//              tiles read B from there, all other nz (further tiles, sparse tail) from L1/L2.
+template <int KC, int WARPS, bool TILES>
+__global__ void __launch_bounds__(WARPS * 32) k_spmm_panel(PanelArgs a, const int* __restrict__ plist) {
+  constexpr int LPR = KC / 4, RPW = 32 / LPR, NW = WARPS * RPW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // dynamic shared memory: [TILES: TS*BW*KC floats] [part: 2*NW*KC floats] [sbuf: NW*2*LPR uint2]
   float* stile = reinterpret_cast<float*>(smem_raw);  // [TS][BW][KC]
+  float* part = reinterpret_cast<float*>(smem_raw) + (TILES ? (size_t)a.TS * a.BW * KC : 0);  // [2][NW][KC]
+  uint2* sbuf = reinterpret_cast<uint2*>(part + 2 * NW * KC);                                   // [NW][2][LPR]
+  __shared__ int P[BH + 1], RS[BH];
+  __shared__ int head_row[NW], tail_row[NW], head_end[NW], w_empty[NW];
   __shared__ uint64_t bar;
   auto tile = cg::tiled_partition<LPR>(cg::this_thread_block());
   const int sl = tile.thread_rank();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / LPR;
-  const int p = blockIdx.x, kc0 = blockIdx.y * KC;
-  const int cnt0 = a.mcsr_cnt[p], delta = a.mcsr_cnt[p + 1] - cnt0, tp = delta - 1;
+  const int w = warp * RPW + sub;
+  const int p = plist ? plist[blockIdx.x] : blockIdx.x, kc0 = blockIdx.y * KC;
+  const int cnt0 = a.mcsr_cnt[p], delta = a.mcsr_cnt[p + 1] - cnt0;
+  const int ntres = TILES ? min(delta - 1, a.TS) : 0;  // tiles resident in shared memory
   const unsigned k4 = a.k / 4;
-  const int c4 = kc0 / 4 + sl;
-  const bool col_ok = c4 < (int)k4;
-  const int kw = min(KC, a.k - kc0);  // floats of this k-chunk that exist
-  const float4* B4 = reinterpret_cast<const float4*>(a.B) + (col_ok ? c4 : 0);
-  const int BW = a.BW, TS = a.TS;
+  const bool col_ok = kc0 / 4 + sl < (int)k4;
+  const int c4 = col_ok ? kc0 / 4 + sl : 0;
+  const int kw = min(KC, a.k - kc0);
+  const float4* B4 = reinterpret_cast<const float4*>(a.B) + c4;
+  float4* C4 = reinterpret_cast<float4*>(a.C) + c4;
+  const int BW = a.BW;
 
-  if (tp > 0 && threadIdx.x == 0) {
-    mbar_init(&bar, 32);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (TILES && ntres > 0) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 32);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {  // producer: one bulk copy per occupied slot; each lane announces its bytes first
+      const int* list = a.mcsr_list + (size_t)(cnt0 - p) * BW;
+      const int nslot = ntres * BW;
+      uint32_t bytes = 0;
+      for (int i = lane; i < nslot; i += 32) bytes += list[i] >= 0 ? (uint32_t)kw * 4u : 0u;
+      mbar_expect_tx_arrive(&bar, bytes);
+      for (int i = lane; i < nslot; i += 32) {
+        const int c = list[i];
+        if (c >= 0) tma_bulk_g2s(stile + (size_t)i * KC, a.B + (size_t)c * a.k + kc0, (uint32_t)kw * 4u, &bar);
+      }
+    }
   }
-  if (tp > 0) __syncthreads();
+  // row table: RS[r] = first handled nz, P = exclusive prefix of handled lengths
+  for (int r = threadIdx.x; r < BH; r += blockDim.x) {
+    const int base = cnt0 * BH + r * delta;
+    const int rs = a.mcsr_e[base], re = a.mcsr_e[base + delta];
+    int nch = 0;
+    if (a.spec_off) nch = a.spec_off[p * BH + r + 1] - a.spec_off[p * BH + r];
+    RS[r] = rs;
+    P[r + 1] = re - rs - nch * STHRESHOLD;
+  }
+  if (threadIdx.x < NW) { head_row[threadIdx.x] = -1; tail_row[threadIdx.x] = -1; head_end[threadIdx.x] = 0; w_empty[threadIdx.x] = 1; }
+  __syncthreads();
+  if (warp == 0) {
+    int v0 = P[4 * lane + 1], v1 = P[4 * lane + 2], v2 = P[4 * lane + 3], v3 = P[4 * lane + 4];
+    int s = v0 + v1 + v2 + v3, inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    int ex = inc - s;
+    if (lane == 0) P[0] = 0;
+    P[4 * lane + 1] = ex + v0; P[4 * lane + 2] = ex + v0 + v1; P[4 * lane + 3] = ex + v0 + v1 + v2; P[4 * lane + 4] = ex + s;
+  }
+  __syncthreads();
+  const int T = P[BH];
 
-  const int rounds = tp > 0 ? (tp + TS - 1) / TS : 1;
-  for (int rd = 0; rd < rounds; ++rd) {
-    const int r0 = rd * TS;
-    const int ntile = tp > 0 ? min(TS, tp - r0) : 0;
-    if (ntile > 0) {
-      if (rd > 0) __syncthreads();  // everybody is done reading the previous round's tiles
-      if (warp == 0) {
-        // producer: one bulk copy per occupied slot; each lane announces its own byte count first
-        const int* list = a.mcsr_list + (size_t)(cnt0 - p + r0) * BW;
-        const int nslot = ntile * BW;
-        uint32_t bytes = 0;
-        for (int i = lane; i < nslot; i += 32) bytes += list[i] >= 0 ? (uint32_t)kw * 4u : 0u;
-        mbar_expect_tx_arrive(&bar, bytes);
-        for (int i = lane; i < nslot; i += 32) {
-          const int c = list[i];
-          if (c >= 0) tma_bulk_g2s(stile + (size_t)i * KC, a.B + (size_t)c * a.k + kc0, (uint32_t)kw * 4u, &bar);
-        }
+  auto finalize = [&](int r, float4 acc) {  // add the row's 512-chunk partials (chunk order) and store
+    const int row = p * BH + r;
+    if (a.spec_off) {
+      const int so = a.spec_off[row], nch = a.spec_off[row + 1] - so;
+      const float4* P4 = reinterpret_cast<const float4*>(a.partial) + (size_t)so * k4 + c4;
+      for (int c = 0; c < nch; ++c) {
+        const float4 pp = P4[(size_t)c * k4];
+        acc.x += pp.x; acc.y += pp.y; acc.z += pp.z; acc.w += pp.w;
       }
-      mbar_wait(&bar, rd & 1);
     }
-    const bool last = rd == rounds - 1;
-    for (int it = 0; it < BH / (PANEL_WARPS * RPW); ++it) {
-      const int r = it * (PANEL_WARPS * RPW) + warp * RPW + sub;
-      const int row = p * BH + r;
-      const int base = cnt0 * BH + r * delta;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rd > 0 && col_ok && row < a.nloc) acc = reinterpret_cast<const float4*>(a.C)[(size_t)row * k4 + c4];
-      int sp_lo = 0, sp_hi = 0, nch = 0;
-      if (last) {
-        sp_lo = a.mcsr_e[base + tp];
-        sp_hi = a.mcsr_e[base + delta];
-        if (a.spec_off) {
-          nch = (sp_hi - sp_lo) / STHRESHOLD;
-          if (nch > 0 && col_ok) {  // fold the chunk partials in, in chunk order
-            const float4* P4 = reinterpret_cast<const float4*>(a.partial) + (size_t)a.spec_off[row] * k4 + c4;
-            for (int c = 0; c < nch; ++c) {
-              const float4 pp = P4[(size_t)c * k4];
-              acc.x += pp.x; acc.y += pp.y; acc.z += pp.z; acc.w += pp.w;
-            }
-          }
-        }
-      }
-      if (ntile > 0) {
-        // dense groups r0..r0+ntile-1 of this row are one contiguous nz range
-        int bnd[MAX_TS + 1];
+    if (col_ok && row < a.nloc) C4[(size_t)row * k4] = acc;
+  };
+
+  // rows without any handled nz (empty, or consumed entirely by 512-chunks)
+  for (int idx = threadIdx.x; idx < BH * LPR; idx += blockDim.x) {
+    const int r = idx / LPR;  // idx % LPR == sl because blockDim is a multiple of LPR
+    if (P[r + 1] == P[r]) finalize(r, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+
+  const int a_pos = (int)((long long)T * w / NW), b_pos = (int)((long long)T * (w + 1) / NW);
+  if (TILES && ntres > 0) mbar_wait(&bar, 0);
+
+  if (a_pos < b_pos) {
+    if (sl == 0) w_empty[w] = 0;
+    int cur = -1;
+    bool cur_started = false;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* S4 = reinterpret_cast<const float4*>(stile) + sl;
+
+    auto load_chunk = [&](int q0, unsigned& off, float& v, int& rrow, bool& st) {
+      const int q = q0 + sl;
+      off = 0; v = 0.f; rrow = 0; st = false;
+      if (q < b_pos) {
+        int lo = 0, hi = BH;  // largest r with P[r] <= q
 #pragma unroll
-        for (int g = 0; g <= MAX_TS; ++g) bnd[g] = g <= ntile ? a.mcsr_e[base + r0 + g] : 0x7fffffff;
-        const int lo = bnd[0], hi = a.mcsr_e[base + r0 + ntile];
-        for (int e0 = lo; e0 < hi; e0 += LPR) {
-          const int e = e0 + sl;
-          unsigned off = 0;
-          float v = 0.f;
-          if (e < hi) {
+        for (int it = 0; it < 7; ++it) {
+          const int mid = (lo + hi) >> 1;
+          if (P[mid] <= q) lo = mid; else hi = mid;
+        }
+        const int e = RS[lo] + (q - P[lo]);
+        const int c = a.csr_e[e];
+        v = a.csr_ev[e];
+        rrow = lo;
+        st = q == P[lo];
+        off = (unsigned)c * k4;
+        if (TILES && ntres > 0) {
+          const int base = cnt0 * BH + lo * delta;
+          if (e < a.mcsr_e[base + ntres]) {
             int g = 0;
-#pragma unroll
-            for (int q = 1; q < MAX_TS; ++q) g += e >= bnd[q];
-            off = (unsigned)(g * BW + (a.csr_e[e] & (BW - 1))) * (KC / 4);
-            v = a.csr_ev[e];
-          }
-          const int cnt = min(LPR, hi - e0);
-          const float4* S4 = reinterpret_cast<const float4*>(stile) + sl;
-          int j = 0;
-          for (; j + 4 <= cnt; j += 4) {
-            const unsigned o0 = tile.shfl(off, j), o1 = tile.shfl(off, j + 1), o2 = tile.shfl(off, j + 2),
-                           o3 = tile.shfl(off, j + 3);
-            const float v0 = tile.shfl(v, j), v1 = tile.shfl(v, j + 1), v2 = tile.shfl(v, j + 2),
-                        v3 = tile.shfl(v, j + 3);
-            const float4 b0 = S4[o0], b1 = S4[o1], b2 = S4[o2], b3 = S4[o3];
-            fma4(acc, v0, b0); fma4(acc, v1, b1); fma4(acc, v2, b2); fma4(acc, v3, b3);
-          }
-          for (; j < cnt; ++j) {
-            const unsigned o = tile.shfl(off, j);
-            const float vv = tile.shfl(v, j);
-            fma4(acc, vv, S4[o]);
+            for (int b = 1; b < ntres; ++b) g += e >= a.mcsr_e[base + b];
+            off = 0x80000000u | (unsigned)((g * BW + (c & (BW - 1))) * (KC / 4));
           }
         }
       }
-      if (last) accum_global<LPR>(tile, sp_lo + nch * STHRESHOLD, sp_hi, a.csr_e, a.csr_ev, B4, k4, acc);
-      if (col_ok && row < a.nloc) reinterpret_cast<float4*>(a.C)[(size_t)row * k4 + c4] = acc;
+    };
+    auto bload = [&](unsigned o) -> float4 {
+      if (TILES && (o & 0x80000000u)) return S4[o & 0x7fffffffu];
+      return ldg4(B4 + o);
+    };
+    auto row_ended = [&]() {  // the pending row `cur` has no more nz in this worker's range
+      if (cur_started) finalize(cur, acc);
+      else {
+        reinterpret_cast<float4*>(part + (size_t)w * KC)[sl] = acc;
+        if (sl == 0) { head_row[w] = cur; head_end[w] = 1; }
+      }
+    };
+
+    // (offset,value) pairs of a chunk are staged in a per-worker shared buffer (double buffered) and
+    // read back two nz at a time with one broadcast LDS.128 -- 0.5 instruction per nz instead of two
+    // shuffles.
+    uint2* sb0 = sbuf + (size_t)w * 2 * LPR;
+    unsigned n_off; float n_v; int n_row; bool n_st;
+    load_chunk(a_pos, n_off, n_v, n_row, n_st);
+    sb0[sl] = make_uint2(n_off, __float_as_uint(n_v));
+    tile.sync();
+    int buf = 0;
+    for (int q0 = a_pos; q0 < b_pos; q0 += LPR) {
+      const int rrow = n_row; const bool st = n_st;
+      const uint2* sb = sb0 + buf * LPR;
+      if (q0 + LPR < b_pos) {
+        load_chunk(q0 + LPR, n_off, n_v, n_row, n_st);
+        sb0[(buf ^ 1) * LPR + sl] = make_uint2(n_off, __float_as_uint(n_v));
+      }
+      const int cnt = min(LPR, b_pos - q0);
+      const unsigned smask = tile.ballot(st);
+      if (cur < 0 && !(smask & 1u)) { cur = tile.shfl(rrow, 0); cur_started = false; }
+      if (smask == 0u && cnt == LPR) {  // whole chunk inside the current row: straight-line code
+#pragma unroll
+        for (int j = 0; j < LPR; j += 8) {
+          const uint4 t0 = *reinterpret_cast<const uint4*>(sb + j), t1 = *reinterpret_cast<const uint4*>(sb + j + 2),
+                      t2 = *reinterpret_cast<const uint4*>(sb + j + 4), t3 = *reinterpret_cast<const uint4*>(sb + j + 6);
+          const float4 b0 = bload(t0.x), b1 = bload(t0.z), b2 = bload(t1.x), b3 = bload(t1.z), b4 = bload(t2.x),
+                       b5 = bload(t2.z), b6 = bload(t3.x), b7 = bload(t3.z);
+          fma4(acc, __uint_as_float(t0.y), b0); fma4(acc, __uint_as_float(t0.w), b1);
+          fma4(acc, __uint_as_float(t1.y), b2); fma4(acc, __uint_as_float(t1.w), b3);
+          fma4(acc, __uint_as_float(t2.y), b4); fma4(acc, __uint_as_float(t2.w), b5);
+          fma4(acc, __uint_as_float(t3.y), b6); fma4(acc, __uint_as_float(t3.w), b7);
+        }
+      } else {
+        int j = 0;
+        while (j < cnt) {
+          if (j + 4 <= cnt && ((smask >> j) & 0xFu) == 0u && (j & 1) == 0) {
+            const uint4 t0 = *reinterpret_cast<const uint4*>(sb + j), t1 = *reinterpret_cast<const uint4*>(sb + j + 2);
+            const float4 b0 = bload(t0.x), b1 = bload(t0.z), b2 = bload(t1.x), b3 = bload(t1.z);
+            fma4(acc, __uint_as_float(t0.y), b0); fma4(acc, __uint_as_float(t0.w), b1);
+            fma4(acc, __uint_as_float(t1.y), b2); fma4(acc, __uint_as_float(t1.w), b3);
+            j += 4;
+            continue;
+          }
+          if ((smask >> j) & 1u) {
+            if (cur >= 0) row_ended();
+            cur = tile.shfl(rrow, j);
+            cur_started = true;
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          const uint2 t = sb[j];
+          fma4(acc, __uint_as_float(t.y), bload(t.x));
+          ++j;
+        }
+      }
+      tile.sync();
+      buf ^= 1;
     }
+    // the row in progress at the end of the range
+    const bool ended = b_pos == P[cur + 1];
+    if (cur_started && ended) finalize(cur, acc);
+    else if (cur_started) {
+      reinterpret_cast<float4*>(part + (size_t)(NW + w) * KC)[sl] = acc;
+      if (sl == 0) tail_row[w] = cur;
+    } else {
+      reinterpret_cast<float4*>(part + (size_t)w * KC)[sl] = acc;
+      if (sl == 0) { head_row[w] = cur; head_end[w] = ended ? 1 : 0; }
+    }
+  }
+  __syncthreads();
+  // rows shared between workers: the worker holding the row's beginning sums the chain in order
+  const int tr = tail_row[w];
+  if (tr >= 0) {
+    float4 tot = reinterpret_cast<const float4*>(part + (size_t)(NW + w) * KC)[sl];
+    for (int w2 = w + 1; w2 < NW; ++w2) {
+      if (w_empty[w2]) continue;
+      if (head_row[w2] != tr) break;
+      const float4 h = reinterpret_cast<const float4*>(part + (size_t)w2 * KC)[sl];
+      tot.x += h.x; tot.y += h.y; tot.z += h.z; tot.w += h.w;
+      if (head_end[w2]) break;
+    }
+    finalize(tr, tot);
   }
 }
 
@@ -313,6 +450,45 @@ int spmm_csr(const uint32_t* rowptr, const uint32_t* col, const float* val, int6
   return FX_OK;
 }
 
+static int panel_warps() {
+  static int w = 0;
+  if (!w) {
+    const char* e = getenv("FLEX_PANEL_WARPS");
+    w = e ? atoi(e) : 16;
+    if (w != 8 && w != 16 && w != 32) w = 16;
+  }
+  return w;
+}
+
+template <int KC, int WARPS>
+static int launch_panels(const fx_aspt_dev& d, const PanelArgs& a, int kchunks, cudaStream_t s) {
+  // per-worker partial slots + (offset,value) staging buffers
+  constexpr int NW = WARPS * (32 / (KC / 4));
+  const size_t work_smem = (size_t)2 * NW * KC * sizeof(float) + (size_t)NW * 2 * (KC / 4) * sizeof(uint2);
+  if (d.n_plain > 0) {
+    static bool carve = false;
+    if (!carve) {
+      FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)work_smem));
+      carve = true;
+    }
+    dim3 grid(d.n_plain, kchunks);
+    k_spmm_panel<KC, WARPS, false><<<grid, WARPS * 32, work_smem, s>>>(a, d.n_tiled ? d.plist_plain : nullptr);
+    FX_LAUNCH_CHECK();
+  }
+  if (d.n_tiled > 0) {
+    const size_t smem = (size_t)a.TS * a.BW * KC * sizeof(float) + work_smem;
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+      FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    dim3 grid(d.n_tiled, kchunks);
+    k_spmm_panel<KC, WARPS, true><<<grid, WARPS * 32, smem, s>>>(a, d.plist_tiled);
+    FX_LAUNCH_CHECK();
+  }
+  return FX_OK;
+}
+
 template <int KC>
 static int launch_aspt(const fx_tiles* t, const PanelArgs& a, int special_p, cudaStream_t s) {
   const fx_aspt_dev& d = t->aspt;
@@ -323,16 +499,11 @@ static int launch_aspt(const fx_tiles* t, const PanelArgs& a, int special_p, cud
     k_spmm_special<KC><<<g, PANEL_WARPS * 32, 0, s>>>(a, d.special, d.special2, special_p, d.partial);
     FX_LAUNCH_CHECK();
   }
-  const size_t smem = (size_t)a.TS * a.BW * KC * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  switch (panel_warps()) {
+    case 8: return launch_panels<KC, 8>(d, a, kchunks, s);
+    case 32: return launch_panels<KC, 32>(d, a, kchunks, s);
+    default: return launch_panels<KC, 16>(d, a, kchunks, s);
   }
-  dim3 grid(d.npanel, kchunks);
-  k_spmm_panel<KC><<<grid, PANEL_WARPS * 32, smem, s>>>(a);
-  FX_LAUNCH_CHECK();
-  return FX_OK;
 }
 
 int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s) {
@@ -349,7 +520,7 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   const size_t tile_bytes = (size_t)d.BW * KC * sizeof(float);
   int ts = d.max_tp;
   if (ts > MAX_TS) ts = MAX_TS;
-  while (ts > 1 && ts * tile_bytes > 200 * 1024) --ts;
+  while (ts > 1 && ts * tile_bytes > 160 * 1024) --ts;  // leave room for the per-worker buffers
   a.TS = ts > 0 ? ts : 1;
   if (d.max_tp == 0) a.TS = 0;
   if (KC == 32) return launch_aspt<32>(t, a, d.special_p, s);
