@@ -74,6 +74,12 @@ void orc_perm_apply(int64_t n, const uint32_t *rowptr, const uint32_t *col, cons
 /* P1 (flex.cu:276-289) */
 void orc_permute_rows(int64_t n, int k, const int32_t *vo_mp, const float *B, float *shadowB);
 
+/* ---- R1-R3: orderings (order_deg.cu, order_rcm.cu, order_gorder.cu, adjlist.cu,
+ *      algo_bfs.cu, unitheap.cu, tools.cu).  rank[u] = new position of u. ---- */
+void orc_order_deg(int64_t n, const uint32_t *rowptr, const uint32_t *col, int desc, uint64_t *rank);
+void orc_order_rcm(int64_t n, const uint32_t *rowptr, const uint32_t *col, uint64_t *rank);
+int orc_order_gorder(int64_t n, const uint32_t *rowptr, const uint32_t *col, int window, uint64_t *rank);
+
 /* ---- A1: ASpT tile builder, canonical (aspt/sspmm_128.cu:831-1087,1207-1333) ---- */
 typedef struct {
   int n, nr, npanel, ne, BH, BW, num_dense;
@@ -101,6 +107,69 @@ void orc_aspt_free(orc_aspt *t);
 /* SpMM evaluated THROUGH the tile structure (dense groups then sparse group per row, one
  * fmaf per nz): the summation order of the GPU panel kernel. C is nr*k. */
 void orc_aspt_spmm(const orc_aspt *t, const float *B, int k, float *C);
+
+/* ---- F1: Flex tile format (mat.cu:1345-1518) ---- */
+typedef struct {
+  int m, tm, tn, ntiles, npanels, nnz;
+  uint32_t *tileRowPtr; /* npanels+1 */
+  uint32_t *tileNnz;    /* ntiles+1 (prefix) */
+  int *nnzTile;         /* ntiles */
+  int *bitMap;          /* ntiles */
+  uint32_t *tileColIdx; /* ntiles */
+  int *rcOffset;        /* nnz: (rowInPanel<<16) | (col - tileColIdx) */
+  float *newVals;       /* nnz */
+} orc_flextile;
+int orc_flex_tile_build(int m, const uint32_t *rowptr, const uint32_t *col, const float *val, int tm,
+                        int tn, int cmajor, orc_flextile *out);
+void orc_flextile_free(orc_flextile *t);
+void orc_flextile_spmm(const orc_flextile *t, const float *B, int k, float *C);
+
+/* ---- F2/F3: row-panel segmentation (mat.cu:1192-1269) ----
+ * Emits the HEAD "alpha" CSR-per-segment layout (pinned against the reference) and the
+ * tile-segment arrays kernels v10-v35 read (reconstructed: their builder is gone from HEAD). */
+typedef struct {
+  int m, tm, nnz, nsegs, rows_total, npanels;
+  uint32_t *alpha_rowPtr;  /* rows_total+1 */
+  uint32_t *alpha_colIdx;  /* nnz */
+  float *alpha_vals;       /* nnz */
+  uint32_t *pillar_rowPtr; /* nsegs+1 */
+  uint32_t *segVoMap;      /* rows_total, MSB = row continues in another segment */
+  int *segs_per_panel;     /* npanels */
+  uint32_t *segPtr;        /* nsegs+1 */
+  uint32_t *segNzRCIdx;    /* 2*nnz: (rowInSeg, absCol), column-major inside a segment */
+  float *segVals;          /* nnz, same order */
+  uint32_t *segVoMapPad;   /* nsegs*tm, missing rows = 0x7fffffff */
+  int *seg_rowPtr;         /* nsegs*(tm+1) */
+  float *segNzCV;          /* 2*nnz: ((float)col, val), row-major inside a segment */
+} orc_seg;
+int orc_seg_build(int m, const uint32_t *rowptr, const uint32_t *col, const float *val,
+                  const int32_t *vo_mp, int tm, int nnz_limit, orc_seg *out);
+void orc_seg_free(orc_seg *s);
+
+/* ---- F4: SM bucketing (mat.cu:1118-1162, row_based_split) ---- */
+void orc_sm_buckets(int n_sm, int nsegs, int npanels, const int *segs_per_panel,
+                    int *next_seg /* n_sm+1 */, int *grouped_tailSeg /* n_sm+1 */);
+
+/* ---- F5: diagonal tiling / pillar format (mat.cu:680-903) ---- */
+typedef struct {
+  int m, nnz, n_sm, n_segs, rows_total, warps_with_weights;
+  uint32_t *alpha_rowPtr;        /* rows_total+1 */
+  uint32_t *alpha_colIdx;
+  float *alpha_vals;
+  uint32_t *alpha_pillar_rowPtr; /* n_segs+1 */
+  uint32_t *alpha_pillarIdx;     /* n_sm+2 */
+  uint32_t *segVoMap;            /* rows_total */
+  float empty_wp_p, band_nz_p;
+} orc_pillar;
+/* returns 0, or <0 where a reference assert / UB would fire (-1 empty row, -2 missing diagonal,
+ * -4 "alpha is too small" :759, -6 empty warp :837, -8 division by zero :862, ...) */
+int orc_diag_tiling(int m, const uint32_t *rowptr, const uint32_t *col, const float *val,
+                    const int32_t *vo_mp, int tm, int n_sm, orc_pillar *out);
+void orc_pillar_free(orc_pillar *p);
+/* alpha_w_atomic_spmm_v36 semantics (flex.cu:4010-4124), serial */
+void orc_alpha_spmm(int rows_total, const uint32_t *alpha_rowPtr, const uint32_t *alpha_colIdx,
+                    const float *alpha_vals, const uint32_t *segVoMap, int64_t m, const float *shadowB,
+                    int k, float *C);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,33 @@ class OrcAspt(C.Structure):
                 ("special2", C.POINTER(C.c_int)), ("regime", C.c_int)]
 
 
+class OrcFlexTile(C.Structure):
+    _fields_ = [("m", C.c_int), ("tm", C.c_int), ("tn", C.c_int), ("ntiles", C.c_int), ("npanels", C.c_int),
+                ("nnz", C.c_int), ("tileRowPtr", C.POINTER(C.c_uint32)), ("tileNnz", C.POINTER(C.c_uint32)),
+                ("nnzTile", C.POINTER(C.c_int)), ("bitMap", C.POINTER(C.c_int)),
+                ("tileColIdx", C.POINTER(C.c_uint32)), ("rcOffset", C.POINTER(C.c_int)),
+                ("newVals", C.POINTER(C.c_float))]
+
+
+class OrcSeg(C.Structure):
+    _fields_ = [("m", C.c_int), ("tm", C.c_int), ("nnz", C.c_int), ("nsegs", C.c_int), ("rows_total", C.c_int),
+                ("npanels", C.c_int), ("alpha_rowPtr", C.POINTER(C.c_uint32)),
+                ("alpha_colIdx", C.POINTER(C.c_uint32)), ("alpha_vals", C.POINTER(C.c_float)),
+                ("pillar_rowPtr", C.POINTER(C.c_uint32)), ("segVoMap", C.POINTER(C.c_uint32)),
+                ("segs_per_panel", C.POINTER(C.c_int)), ("segPtr", C.POINTER(C.c_uint32)),
+                ("segNzRCIdx", C.POINTER(C.c_uint32)), ("segVals", C.POINTER(C.c_float)),
+                ("segVoMapPad", C.POINTER(C.c_uint32)), ("seg_rowPtr", C.POINTER(C.c_int)),
+                ("segNzCV", C.POINTER(C.c_float))]
+
+
+class OrcPillar(C.Structure):
+    _fields_ = [("m", C.c_int), ("nnz", C.c_int), ("n_sm", C.c_int), ("n_segs", C.c_int), ("rows_total", C.c_int),
+                ("warps_with_weights", C.c_int), ("alpha_rowPtr", C.POINTER(C.c_uint32)),
+                ("alpha_colIdx", C.POINTER(C.c_uint32)), ("alpha_vals", C.POINTER(C.c_float)),
+                ("alpha_pillar_rowPtr", C.POINTER(C.c_uint32)), ("alpha_pillarIdx", C.POINTER(C.c_uint32)),
+                ("segVoMap", C.POINTER(C.c_uint32)), ("empty_wp_p", C.c_float), ("band_nz_p", C.c_float)]
+
+
 def build():
     """Compile oracle/*.c into liborc.so (gcc).  Building the checker is not using it."""
     subprocess.check_call(["make", "-s", "-C", _HERE])
@@ -82,6 +109,19 @@ def lib():
     L.orc_aspt_free.argtypes = [C.POINTER(OrcAspt)]
     L.orc_aspt_spmm.argtypes = [C.POINTER(OrcAspt), f32p, C.c_int, f32p]
     L.orc_num_threads.restype = C.c_int
+    L.orc_order_deg.argtypes = [C.c_int64, u32p, u32p, C.c_int, u64p]
+    L.orc_order_rcm.argtypes = [C.c_int64, u32p, u32p, u64p]
+    L.orc_order_gorder.argtypes = [C.c_int64, u32p, u32p, C.c_int, u64p]
+    L.orc_order_gorder.restype = C.c_int
+    L.orc_flex_tile_build.argtypes = [C.c_int, u32p, u32p, f32p, C.c_int, C.c_int, C.c_int, C.POINTER(OrcFlexTile)]
+    L.orc_flextile_free.argtypes = [C.POINTER(OrcFlexTile)]
+    L.orc_flextile_spmm.argtypes = [C.POINTER(OrcFlexTile), f32p, C.c_int, f32p]
+    L.orc_seg_build.argtypes = [C.c_int, u32p, u32p, f32p, i32p, C.c_int, C.c_int, C.POINTER(OrcSeg)]
+    L.orc_seg_free.argtypes = [C.POINTER(OrcSeg)]
+    L.orc_sm_buckets.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, i32p]
+    L.orc_diag_tiling.argtypes = [C.c_int, u32p, u32p, f32p, i32p, C.c_int, C.c_int, C.POINTER(OrcPillar)]
+    L.orc_pillar_free.argtypes = [C.POINTER(OrcPillar)]
+    L.orc_alpha_spmm.argtypes = [C.c_int, u32p, u32p, f32p, u32p, C.c_int64, f32p, C.c_int, f32p]
     _LIB = L
     return L
 
@@ -189,6 +229,22 @@ def permute_rows(vo_mp, B):
     return out
 
 
+def order(kind, rowptr, col, window=3):
+    """rank[old] = new for kind in deg|rcm|gor (DataLoaderDeg/Rcm/Gorder use deg DESC, rcm, gorder w=3)."""
+    rowptr = np.ascontiguousarray(rowptr, np.uint32)
+    col = np.ascontiguousarray(col, np.uint32)
+    n = len(rowptr) - 1
+    rank = np.empty(n, np.uint64)
+    if kind == "deg":
+        lib().orc_order_deg(n, rowptr, col, 1, rank)
+    elif kind == "rcm":
+        lib().orc_order_rcm(n, rowptr, col, rank)
+    else:
+        if lib().orc_order_gorder(n, rowptr, col, window, rank) != 0:
+            raise ValueError("gorder: isolated vertex")
+    return rank
+
+
 class Aspt:
     """Canonical ASpT tile metadata as numpy arrays (copied out of the C struct)."""
 
@@ -230,3 +286,81 @@ class Aspt:
             lib().orc_aspt_free(C.byref(self._t))
         except Exception:
             pass
+
+
+def flex_tile(rowptr, col, val, tm, tn, cmajor):
+    """F1 (mat.cu:1345-1518) -> dict of arrays; raises ValueError on an empty row."""
+    rowptr, col, val = _csr(rowptr, col, val)
+    t = OrcFlexTile()
+    if lib().orc_flex_tile_build(len(rowptr) - 1, rowptr, col, val, tm, tn, int(cmajor), C.byref(t)) != 0:
+        raise ValueError("empty row")
+    nt, nnz = t.ntiles, t.nnz
+    out = dict(ntiles=nt, npanels=t.npanels, tileRowPtr=_arr(t.tileRowPtr, t.npanels + 1, np.uint32),
+               tileNnz=_arr(t.tileNnz, nt + 1, np.uint32), nnzTile=_arr(t.nnzTile, nt, np.int32),
+               bitMap=_arr(t.bitMap, nt, np.int32), tileColIdx=_arr(t.tileColIdx, nt, np.uint32),
+               rcOffset=_arr(t.rcOffset, nnz, np.int32), newVals=_arr(t.newVals, nnz, np.float32))
+    lib().orc_flextile_free(C.byref(t))
+    return out
+
+
+def flextile_spmm(rowptr, col, val, tm, tn, cmajor, B):
+    rowptr, col, val = _csr(rowptr, col, val)
+    t = OrcFlexTile()
+    assert lib().orc_flex_tile_build(len(rowptr) - 1, rowptr, col, val, tm, tn, int(cmajor), C.byref(t)) == 0
+    out = np.empty((len(rowptr) - 1, B.shape[1]), np.float32)
+    lib().orc_flextile_spmm(C.byref(t), np.ascontiguousarray(B, np.float32).ravel(), B.shape[1], out.ravel())
+    lib().orc_flextile_free(C.byref(t))
+    return out
+
+
+def seg(rowptr, col, val, vo_mp, tm, nnz_limit=128):
+    """F2/F3 (mat.cu:1192-1269) -> dict of arrays."""
+    rowptr, col, val = _csr(rowptr, col, val)
+    s = OrcSeg()
+    if lib().orc_seg_build(len(rowptr) - 1, rowptr, col, val, np.ascontiguousarray(vo_mp, np.int32), tm, nnz_limit,
+                           C.byref(s)) != 0:
+        raise ValueError("empty row")
+    S, nnz, R = s.nsegs, s.nnz, s.rows_total
+    out = dict(nsegs=S, rows_total=R, npanels=s.npanels, alpha_rowPtr=_arr(s.alpha_rowPtr, R + 1, np.uint32),
+               alpha_colIdx=_arr(s.alpha_colIdx, nnz, np.uint32), alpha_vals=_arr(s.alpha_vals, nnz, np.float32),
+               alpha_pillar_rowPtr=_arr(s.pillar_rowPtr, S + 1, np.uint32), segVoMap=_arr(s.segVoMap, R, np.uint32),
+               segs_per_panel=_arr(s.segs_per_panel, s.npanels, np.int32), segPtr=_arr(s.segPtr, S + 1, np.uint32),
+               segNzRCIdx=_arr(s.segNzRCIdx, 2 * nnz, np.uint32), segVals=_arr(s.segVals, nnz, np.float32),
+               segVoMapPad=_arr(s.segVoMapPad, S * tm, np.uint32), seg_rowPtr=_arr(s.seg_rowPtr, S * (tm + 1), np.int32),
+               segNzCV=_arr(s.segNzCV, 2 * nnz, np.float32))
+    lib().orc_seg_free(C.byref(s))
+    return out
+
+
+def sm_buckets(n_sm, nsegs, segs_per_panel):
+    spp = np.ascontiguousarray(segs_per_panel, np.int32)
+    nx = np.empty(n_sm + 1, np.int32)
+    tl = np.empty(n_sm + 1, np.int32)
+    lib().orc_sm_buckets(n_sm, nsegs, len(spp), spp, nx, tl)
+    return nx, tl
+
+
+def diag_tiling(rowptr, col, val, vo_mp, tm, n_sm):
+    """F5 (mat.cu:680-903) -> dict of arrays; raises ValueError(code) where the reference asserts."""
+    rowptr, col, val = _csr(rowptr, col, val)
+    p = OrcPillar()
+    rc = lib().orc_diag_tiling(len(rowptr) - 1, rowptr, col, val, np.ascontiguousarray(vo_mp, np.int32), tm, n_sm,
+                               C.byref(p))
+    if rc != 0:
+        raise ValueError(rc)
+    R, nnz = p.rows_total, p.nnz
+    out = dict(n_segs=p.n_segs, rows_total=R, warps_with_weights=p.warps_with_weights, empty_wp_p=p.empty_wp_p,
+               band_nz_p=p.band_nz_p, alpha_rowPtr=_arr(p.alpha_rowPtr, R + 1, np.uint32),
+               alpha_colIdx=_arr(p.alpha_colIdx, nnz, np.uint32), alpha_vals=_arr(p.alpha_vals, nnz, np.float32),
+               alpha_pillar_rowPtr=_arr(p.alpha_pillar_rowPtr, p.n_segs + 1, np.uint32),
+               alpha_pillarIdx=_arr(p.alpha_pillarIdx, n_sm + 2, np.uint32), segVoMap=_arr(p.segVoMap, R, np.uint32))
+    lib().orc_pillar_free(C.byref(p))
+    return out
+
+
+def alpha_spmm(alpha, m, shadowB):
+    k = shadowB.shape[1]
+    out = np.empty((m, k), np.float32)
+    lib().orc_alpha_spmm(alpha["rows_total"], alpha["alpha_rowPtr"], alpha["alpha_colIdx"], alpha["alpha_vals"],
+                         alpha["segVoMap"], m, np.ascontiguousarray(shadowB, np.float32).ravel(), k, out.ravel())
+    return out
