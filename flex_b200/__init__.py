@@ -44,7 +44,7 @@ class MatrixInfo(C.Structure):
 class BuildOpts(C.Structure):
     _fields_ = [("format", C.c_int32), ("tm", C.c_int32), ("tn", C.c_int32), ("bw", C.c_int32),
                 ("nnz_limit", C.c_int32), ("n_sm", C.c_int32), ("row_begin", C.c_int32),
-                ("row_end", C.c_int32), ("reserved", C.c_int32 * 8)]
+                ("row_end", C.c_int32), ("cmajor", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
 class AsptArrays(C.Structure):
@@ -60,6 +60,36 @@ class AsptArrays(C.Structure):
                 ("csr_ev", C.POINTER(C.c_float))]
 
 
+class TileArrays(C.Structure):
+    _fields_ = [("m", C.c_int32), ("tm", C.c_int32), ("tn", C.c_int32), ("ntiles", C.c_int32),
+                ("npanels", C.c_int32), ("nnz", C.c_int32), ("cmajor", C.c_int32),
+                ("tileRowPtr", C.POINTER(C.c_uint32)), ("tileNnz", C.POINTER(C.c_uint32)),
+                ("nnzTile", C.POINTER(C.c_int32)), ("bitMap", C.POINTER(C.c_int32)),
+                ("tileColIdx", C.POINTER(C.c_uint32)), ("rcOffset", C.POINTER(C.c_int32)),
+                ("newVals", C.POINTER(C.c_float))]
+
+
+class SegArrays(C.Structure):
+    _fields_ = [("m", C.c_int32), ("tm", C.c_int32), ("nnz", C.c_int32), ("nsegs", C.c_int32),
+                ("rows_total", C.c_int32), ("npanels", C.c_int32), ("n_sm", C.c_int32),
+                ("alpha_rowPtr", C.POINTER(C.c_uint32)), ("alpha_colIdx", C.POINTER(C.c_uint32)),
+                ("alpha_pillar_rowPtr", C.POINTER(C.c_uint32)), ("segVoMap", C.POINTER(C.c_uint32)),
+                ("alpha_vals", C.POINTER(C.c_float)), ("segs_per_panel", C.POINTER(C.c_int32)),
+                ("segPtr", C.POINTER(C.c_uint32)), ("segNzRCIdx", C.POINTER(C.c_uint32)),
+                ("segVoMapPad", C.POINTER(C.c_uint32)), ("segVals", C.POINTER(C.c_float)),
+                ("segNzCV", C.POINTER(C.c_float)), ("seg_rowPtr", C.POINTER(C.c_int32)),
+                ("next_seg", C.POINTER(C.c_int32)), ("grouped_tailSeg", C.POINTER(C.c_int32))]
+
+
+class PillarArrays(C.Structure):
+    _fields_ = [("m", C.c_int32), ("nnz", C.c_int32), ("n_sm", C.c_int32), ("n_segs", C.c_int32),
+                ("rows_total", C.c_int32), ("warps_with_weights", C.c_int32),
+                ("alpha_rowPtr", C.POINTER(C.c_uint32)), ("alpha_colIdx", C.POINTER(C.c_uint32)),
+                ("alpha_pillar_rowPtr", C.POINTER(C.c_uint32)), ("alpha_pillarIdx", C.POINTER(C.c_uint32)),
+                ("segVoMap", C.POINTER(C.c_uint32)), ("alpha_vals", C.POINTER(C.c_float)),
+                ("empty_wp_p", C.c_float), ("band_nz_p", C.c_float)]
+
+
 class Report(C.Structure):
     _fields_ = [("tPre_ms", C.c_float), ("tElap_ms", C.c_float), ("gflops", C.c_double),
                 ("tpre_over_telap", C.c_double), ("errs_flex", C.c_int64),
@@ -72,7 +102,7 @@ ABI_SYMBOLS = [
     "fx_csr_from_arrays", "fx_csr_from_device", "fx_matrix_get_info", "fx_matrix_host_csr",
     "fx_matrix_device_csr", "fx_matrix_free", "fx_rand_B", "fx_reorder", "fx_reorder_with_rank",
     "fx_permutation", "fx_permute_rows", "fx_unpermute_rows", "fx_build", "fx_rebuild",
-    "fx_tiles_export_aspt", "fx_tiles_free", "fx_spmm", "fx_spmm_host", "fx_check",
+    "fx_tiles_export_aspt", "fx_tiles_export_tile", "fx_tiles_export_seg", "fx_tiles_export_pillar", "fx_tiles_free", "fx_spmm", "fx_spmm_host", "fx_check",
 ]
 
 
@@ -106,6 +136,9 @@ def lib():
     L.fx_build.argtypes = [vp, C.POINTER(BuildOpts), C.POINTER(vp), C.POINTER(C.c_float)]
     L.fx_rebuild.argtypes = [vp, C.POINTER(C.c_float)]
     L.fx_tiles_export_aspt.argtypes = [vp, C.POINTER(AsptArrays)]
+    L.fx_tiles_export_tile.argtypes = [vp, C.POINTER(TileArrays)]
+    L.fx_tiles_export_seg.argtypes = [vp, C.POINTER(SegArrays)]
+    L.fx_tiles_export_pillar.argtypes = [vp, C.POINTER(PillarArrays)]
     L.fx_tiles_free.argtypes = [vp]
     L.fx_tiles_free.restype = None
     L.fx_spmm.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(C.c_float)]
@@ -245,12 +278,12 @@ class Mat:
     """Tile format built on the GPU (Mat::Mat + csr2tile/transfer/launch_prep, mat.cuh:74-182;
     ASpT: the pre-process section of process(), aspt/sspmm_128.cu:1207-1333)."""
 
-    def __init__(self, dl, fmt="aspt", tm=4, tn=4, bw=0, row_begin=0, row_end=0, n_sm=0):
+    def __init__(self, dl, fmt="aspt", tm=4, tn=4, bw=0, row_begin=0, row_end=0, n_sm=0, cmajor=0, nnz_limit=0):
         self.dl = dl
         self._h = C.c_void_p()
         o = BuildOpts()
         o.format = _FMT[fmt] if isinstance(fmt, str) else int(fmt)
-        o.tm, o.tn, o.bw, o.n_sm = tm, tn, bw, n_sm
+        o.tm, o.tn, o.bw, o.n_sm, o.cmajor, o.nnz_limit = tm, tn, bw, n_sm, int(cmajor), nnz_limit
         o.row_begin, o.row_end = row_begin, row_end
         self.fmt = o.format
         self.row_begin = row_begin
@@ -280,6 +313,46 @@ class Mat:
                    special=_np(a.special, a.special_p, np.int32).copy(),
                    special2=_np(a.special2, a.special_p, np.int32).copy())
         return out
+
+    def export_tile(self):
+        a = TileArrays()
+        _ck(lib().fx_tiles_export_tile(self._h, C.byref(a)))
+        nt, nnz = a.ntiles, a.nnz
+        return dict(ntiles=nt, npanels=a.npanels, tileRowPtr=_np(a.tileRowPtr, a.npanels + 1, np.uint32).copy(),
+                    tileNnz=_np(a.tileNnz, nt + 1, np.uint32).copy(), nnzTile=_np(a.nnzTile, nt, np.int32).copy(),
+                    bitMap=_np(a.bitMap, nt, np.int32).copy(), tileColIdx=_np(a.tileColIdx, nt, np.uint32).copy(),
+                    rcOffset=_np(a.rcOffset, nnz, np.int32).copy(), newVals=_np(a.newVals, nnz, np.float32).copy())
+
+    def export_seg(self):
+        a = SegArrays()
+        _ck(lib().fx_tiles_export_seg(self._h, C.byref(a)))
+        S, R, nnz, tm = a.nsegs, a.rows_total, a.nnz, a.tm
+        return dict(nsegs=S, rows_total=R, npanels=a.npanels, n_sm=a.n_sm,
+                    alpha_rowPtr=_np(a.alpha_rowPtr, R + 1, np.uint32).copy(),
+                    alpha_colIdx=_np(a.alpha_colIdx, nnz, np.uint32).copy(),
+                    alpha_vals=_np(a.alpha_vals, nnz, np.float32).copy(),
+                    alpha_pillar_rowPtr=_np(a.alpha_pillar_rowPtr, S + 1, np.uint32).copy(),
+                    segVoMap=_np(a.segVoMap, R, np.uint32).copy(),
+                    segs_per_panel=_np(a.segs_per_panel, a.npanels, np.int32).copy(),
+                    segPtr=_np(a.segPtr, S + 1, np.uint32).copy(), segNzRCIdx=_np(a.segNzRCIdx, 2 * nnz, np.uint32).copy(),
+                    segVals=_np(a.segVals, nnz, np.float32).copy(), segVoMapPad=_np(a.segVoMapPad, S * tm, np.uint32).copy(),
+                    seg_rowPtr=_np(a.seg_rowPtr, S * (tm + 1), np.int32).copy(),
+                    segNzCV=_np(a.segNzCV, 2 * nnz, np.float32).copy(),
+                    next_seg=_np(a.next_seg, a.n_sm + 1, np.int32).copy(),
+                    grouped_tailSeg=_np(a.grouped_tailSeg, a.n_sm + 1, np.int32).copy())
+
+    def export_pillar(self):
+        a = PillarArrays()
+        _ck(lib().fx_tiles_export_pillar(self._h, C.byref(a)))
+        R, nnz = a.rows_total, a.nnz
+        return dict(n_segs=a.n_segs, rows_total=R, warps_with_weights=a.warps_with_weights,
+                    empty_wp_p=a.empty_wp_p, band_nz_p=a.band_nz_p,
+                    alpha_rowPtr=_np(a.alpha_rowPtr, R + 1, np.uint32).copy(),
+                    alpha_colIdx=_np(a.alpha_colIdx, nnz, np.uint32).copy(),
+                    alpha_vals=_np(a.alpha_vals, nnz, np.float32).copy(),
+                    alpha_pillar_rowPtr=_np(a.alpha_pillar_rowPtr, a.n_segs + 1, np.uint32).copy(),
+                    alpha_pillarIdx=_np(a.alpha_pillarIdx, a.n_sm + 2, np.uint32).copy(),
+                    segVoMap=_np(a.segVoMap, R, np.uint32).copy())
 
     def spmm(self, B_ptr, C_ptr, k, stream=None, timed=False):
         """C = A*B on device pointers.  timed=True returns tElap in ms (events + sync)."""

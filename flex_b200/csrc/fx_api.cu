@@ -31,6 +31,7 @@ int build_dispatch(fx_tiles* t, cudaStream_t s) {
   switch (t->format) {
     case FX_FMT_CSR: return FX_OK;
     case FX_FMT_ASPT: return fx::aspt_build(t, s);
+    case FX_FMT_TILE: case FX_FMT_SEG: case FX_FMT_PILLAR: return fx::flex_build(t, s);
     default: fx::set_error("format %d not built by this entry point", t->format); return FX_ERR_UNSUPPORTED;
   }
 }
@@ -76,9 +77,12 @@ extern "C" int fx_build(const fx_matrix* m, const fx_build_opts* opts, fx_tiles*
     if (a.BW != 128 && a.BW != 256) { fx::set_error("bw must be 128 or 256"); return fail(FX_ERR_ARG); }
     rc = fx::aspt_carve(t, m->n);
     if (rc != FX_OK) return fail(rc);
+  } else if (t->format == FX_FMT_TILE || t->format == FX_FMT_SEG || t->format == FX_FMT_PILLAR) {
+    rc = fx::flex_carve(t);
+    if (rc != FX_OK) return fail(rc);
   } else if (t->format != FX_FMT_CSR) {
-    fx::set_error("fx_build: format %d is built through fx_flex_build", t->format);
-    return fail(FX_ERR_UNSUPPORTED);
+    fx::set_error("fx_build: unknown format %d", t->format);
+    return fail(FX_ERR_ARG);
   }
   rc = time_region(t, t->own_stream, tPre_ms, build_dispatch);
   if (rc != FX_OK) return fail(rc);
@@ -93,6 +97,7 @@ extern "C" int fx_rebuild(fx_tiles* t, float* tPre_ms) {
 
 extern "C" void fx_tiles_free(fx_tiles* t) {
   if (!t) return;
+  fx::flex_release(t);
   t->arena.release();
   if (t->ev0) cudaEventDestroy(t->ev0);
   if (t->ev1) cudaEventDestroy(t->ev1);
@@ -145,11 +150,12 @@ extern "C" int fx_tiles_export_aspt(fx_tiles* t, fx_aspt_arrays* o) {
 
 static int spmm_dispatch(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s) {
   const fx_matrix* m = t->mat;
-  if (t->format == FX_FMT_CSR || k % 4 != 0) {
+  if (t->format == FX_FMT_CSR || (k % 4 != 0 && t->format == FX_FMT_ASPT)) {
     // raw CSR over the shard's rows (run_ge_spmm path flex.cu:4285; "ssparse" regime :629)
     return fx::spmm_csr(m->rowptr_dev + t->row_begin, m->col_dev, m->val_dev, t->row_end - t->row_begin, B, C, k, s);
   }
   if (t->format == FX_FMT_ASPT) return fx::spmm_aspt(t, B, C, k, s);
+  if (t->format == FX_FMT_TILE || t->format == FX_FMT_SEG || t->format == FX_FMT_PILLAR) return fx::flex_spmm(t, B, C, k, s);
   fx::set_error("fx_spmm: format %d has its own entry point", t->format);
   return FX_ERR_UNSUPPORTED;
 }

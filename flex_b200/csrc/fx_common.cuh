@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/flexb200.h"
+#include "fx_flex.cuh"
 
 namespace fx {
 
@@ -135,6 +136,7 @@ struct fx_tiles {
   int64_t nnz_local = 0;
   fx::Arena arena;
   fx_aspt_dev aspt;
+  fx_flex_dev flex;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned long long* stats_host = nullptr;  // pinned mirror of aspt.stats
   // host staging for fx_spmm_host
@@ -153,6 +155,11 @@ int ensure_device(const fx_matrix* m);
 size_t aspt_arena_bytes(int64_t n_rows, int64_t ncols, int64_t ne, int BW, int k, int G);
 int aspt_carve(fx_tiles* t, int64_t ncols);
 int aspt_build(fx_tiles* t, cudaStream_t s);
+// fx_flex_build.cu
+int flex_carve(fx_tiles* t);
+int flex_build(fx_tiles* t, cudaStream_t s);
+int flex_spmm(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s);
+void flex_release(fx_tiles* t);
 // fx_spmm.cu
 int spmm_csr(const uint32_t* rowptr, const uint32_t* col, const float* val, int64_t nrows, const float* B,
              float* C, int k, cudaStream_t s);

@@ -1,0 +1,684 @@
+// fx_flex_build.cu -- builders of the Flex formats (mat.cu) and the SpMM kernels that consume them.
+//
+//   FX_FMT_TILE   csr2flex_Rmajor / csr2flex_Cmajor   mat.cu:1345-1518   GPU builder
+//   FX_FMT_SEG    csr2seg_Cmajor + SM buckets         mat.cu:1192-1269, 1118-1162   GPU builder
+//   FX_FMT_PILLAR csr2_DiagTiling                     mat.cu:680-903    host round 1-2 + GPU-free round 3
+//
+// GPU builders: one cooperative tile of TM lanes per row panel, lane i owning row i's cursor; a step
+// of the reference's sequential sweep (next flexible-origin tile / next distinct column) becomes a
+// min-reduction + ballot over the TM lanes.  Two passes (count, then write at scanned offsets), no
+// host round trip except the totals.  Layouts are bit-identical to the reference's.
+//
+// SpMM: k_spmm_panel_acc streams a panel's nz in the stored order and accumulates the panel's tm rows
+// of C in shared memory (one store per C element, deterministic -- the reference's v10-v35 kernels
+// use fp32 atomics for rows split across segments).  k_spmm_alpha is the pillar-format kernel
+// (alpha_w_atomic_spmm_v36, flex.cu:4010-4124): SM-affine pillar queues + shared balance queue,
+// store or atomicAdd by the MSB of segVoMap.
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+#include <cooperative_groups/scan.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "fx_common.cuh"
+#include "fx_flex.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr unsigned NOCOL = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// F2/F3: row-panel segmentation
+// ---------------------------------------------------------------------------------------------
+struct SegOut {
+  unsigned *alpha_rowPtr, *alpha_colIdx, *pillar_rowPtr, *segVoMap;
+  float* alpha_vals;
+  unsigned *segPtr, *segNzRCIdx, *segVoMapPad;
+  float *segVals, *segNzCV;
+  int* seg_rowPtr;
+};
+
+template <int TM, bool WRITE>
+__global__ void __launch_bounds__(128) k_seg(const unsigned* __restrict__ rowptr, const unsigned* __restrict__ col,
+                                             const float* __restrict__ val, const int* __restrict__ vo_mp, int m,
+                                             int npanels, int nnz_limit, int* __restrict__ segs_per_panel,
+                                             const int* __restrict__ seg_off, SegOut o) {
+  auto tile = cg::tiled_partition<TM>(cg::this_thread_block());
+  const int lane = tile.thread_rank();
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) / TM;
+  if (p >= npanels) return;
+  const int rowStart = p * TM, rowEnd = min(m, rowStart + TM), rows = rowEnd - rowStart;
+  const int dif = (int)(0.1 * nnz_limit);
+  const bool has_row = lane < rows;
+  const int row = rowStart + lane;
+  const unsigned rs = has_row ? rowptr[row] : 0, re = has_row ? rowptr[row + 1] : 0;
+  unsigned cur = rs, prev = rs;
+  const unsigned panel_base = rowptr[rowStart];
+  int emitted = 0, nnzInSeg = 0, nseg = 0, atom = 0;
+  int remaining = (int)(rowptr[rowEnd] - panel_base);
+  const int s0 = WRITE ? seg_off[p] : 0;
+  while (remaining > 0 || nnzInSeg > 0) {
+    if (remaining > 0) {
+      const unsigned c = cur < re ? col[cur] : NOCOL;
+      const unsigned j = cg::reduce(tile, c, cg::less<unsigned>());
+      const bool take = c == j;
+      const unsigned bal = tile.ballot(take);
+      if (take) {
+        if (WRITE) {  // C-major stream: position in consumption order
+          const unsigned pos = panel_base + emitted + nnzInSeg + __popc(bal & ((1u << lane) - 1u));
+          o.segNzRCIdx[2 * (size_t)pos] = lane;
+          o.segNzRCIdx[2 * (size_t)pos + 1] = c;
+          o.segVals[pos] = val[cur];
+        }
+        ++cur; ++atom;
+      }
+      const int took = __popc(bal);
+      nnzInSeg += took; remaining -= took;
+    }
+    if ((remaining == 0 && nnzInSeg) || (nnz_limit - nnzInSeg) <= dif || nnzInSeg > nnz_limit) {  // mat.cu:1235
+      if (WRITE) {
+        const int s = s0 + nseg;
+        const int cnt = (int)(cur - prev);
+        const int ex = cg::exclusive_scan(tile, cnt);
+        const unsigned seg_base = panel_base + emitted;
+        const size_t rbase = (size_t)s0 * TM + (size_t)nseg * rows;  // every earlier panel has TM rows
+        if (has_row) {
+          o.alpha_rowPtr[rbase + lane] = seg_base + ex;
+          for (int q = 0; q < cnt; ++q) {
+            const unsigned cc = col[prev + q];
+            const float vv = val[prev + q];
+            o.alpha_colIdx[seg_base + ex + q] = cc;
+            o.alpha_vals[seg_base + ex + q] = vv;
+            o.segNzCV[2 * (size_t)(seg_base + ex + q)] = (float)cc;
+            o.segNzCV[2 * (size_t)(seg_base + ex + q) + 1] = vv;
+          }
+          const unsigned v = (unsigned)vo_mp[row];
+          o.segVoMap[rbase + lane] = atom < (int)(re - rs) ? (v | 0x80000000u) : v;  // mat.cu:1252-1260
+        }
+        o.segVoMapPad[(size_t)s * TM + lane] = has_row ? ((unsigned)vo_mp[row] | (atom < (int)(re - rs) ? 0x80000000u : 0u))
+                                                       : 0x7fffffffu;
+        o.seg_rowPtr[(size_t)s * (TM + 1) + lane] = has_row ? ex : nnzInSeg;
+        if (lane == 0) {
+          o.seg_rowPtr[(size_t)s * (TM + 1) + TM] = nnzInSeg;
+          o.pillar_rowPtr[s] = (unsigned)rbase;
+          o.segPtr[s] = seg_base;
+        }
+      }
+      emitted += nnzInSeg;
+      nnzInSeg = 0; atom = 0; prev = cur;
+      ++nseg;
+    }
+  }
+  if (!WRITE && lane == 0) segs_per_panel[p] = nseg;
+}
+
+// exclusive scan of a small int array by one CTA (npanels up to ~1M): out[n] = total
+__global__ void __launch_bounds__(1024) k_scan_int(const int* __restrict__ in, int n, int* __restrict__ out) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  auto warp = cg::tiled_partition<32>(cg::this_thread_block());
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? in[i] : 0;
+    const int inc = cg::inclusive_scan(warp, v);
+    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int ws = warp_sum[threadIdx.x];
+      const int wi = cg::inclusive_scan(warp, ws);
+      warp_sum[threadIdx.x] = wi - ws;
+    }
+    __syncthreads();
+    const int incl = carry_s + warp_sum[threadIdx.x >> 5] + inc;
+    if (i < n) out[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+__global__ void k_seg_tail(SegOut o, int nsegs, int rows_total, unsigned nnz) {
+  o.alpha_rowPtr[rows_total] = nnz;
+  o.pillar_rowPtr[nsegs] = (unsigned)rows_total;
+  o.segPtr[nsegs] = nnz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// F1: flexible-origin tiles
+// ---------------------------------------------------------------------------------------------
+struct TileOut {
+  unsigned *tileRowPtr, *tileNnz, *tileColIdx;
+  int *nnzTile, *bitMap, *rcOffset;
+  float* newVals;
+};
+
+template <int TM, bool WRITE>
+__global__ void __launch_bounds__(128) k_tile(const unsigned* __restrict__ rowptr, const unsigned* __restrict__ col,
+                                              const float* __restrict__ val, int m, int n, int npanels, int tn,
+                                              int cmajor, int* __restrict__ tiles_per_panel,
+                                              const int* __restrict__ tile_off, TileOut o) {
+  auto tile = cg::tiled_partition<TM>(cg::this_thread_block());
+  const int lane = tile.thread_rank();
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) / TM;
+  if (p >= npanels) return;
+  const int rowStart = p * TM, rowEnd = min(m, rowStart + TM), rows = rowEnd - rowStart;
+  const bool has_row = lane < rows;
+  const unsigned rs = has_row ? rowptr[rowStart + lane] : 0, re = has_row ? rowptr[rowStart + lane + 1] : 0;
+  unsigned cur = rs;
+  unsigned pos = rowptr[rowStart];
+  const unsigned pend = rowptr[rowEnd];
+  int nt = 0;
+  const int t0 = WRITE ? tile_off[p] : 0;
+  while (pos < pend) {
+    const unsigned c0 = cur < re ? col[cur] : NOCOL;
+    const unsigned left = cg::reduce(tile, c0, cg::less<unsigned>());
+    const unsigned right = min(left + (unsigned)tn, (unsigned)n);
+    // this row's entries inside [left,right)
+    unsigned e = cur;
+    unsigned bits = 0;
+    while (e < re && col[e] < right) { bits |= 1u << (col[e] - left); ++e; }
+    const int cnt = (int)(e - cur);
+    const int total = cg::reduce(tile, cnt, cg::plus<int>());
+    if (WRITE) {
+      unsigned bm = bits;
+      for (int o2 = TM / 2; o2 > 0; o2 >>= 1) bm |= tile.shfl_xor(bm, o2);
+      if (!cmajor) {
+        const int ex = cg::exclusive_scan(tile, cnt);
+        for (int q = 0; q < cnt; ++q) {
+          o.rcOffset[pos + ex + q] = (lane << 16) | (int)(col[cur + q] - left);
+          o.newVals[pos + ex + q] = val[cur + q];
+        }
+      } else {
+        // (column, row) order: entries of earlier columns first, then earlier rows of the same column
+        unsigned before = 0;  // running count of entries in columns < current
+        unsigned q = cur;
+        for (int ci = 0; ci < tn; ++ci) {
+          const bool mine = q < e && col[q] == left + ci;
+          const unsigned bal = tile.ballot(mine);
+          if (mine) {
+            const unsigned w = pos + before + __popc(bal & ((1u << lane) - 1u));
+            o.rcOffset[w] = (lane << 16) | ci;
+            o.newVals[w] = val[q];
+            ++q;
+          }
+          before += __popc(bal);
+        }
+      }
+      if (lane == 0) {
+        const int t = t0 + nt;
+        o.nnzTile[t] = total;
+        o.bitMap[t] = (int)bm;
+        o.tileNnz[t] = pos;  // prefix: tileNnz[t] = nz before tile t
+        o.tileColIdx[t] = left;
+      }
+    }
+    cur = e;
+    pos += total;
+    ++nt;
+  }
+  if (!WRITE && lane == 0) tiles_per_panel[p] = nt;
+}
+
+__global__ void k_tile_tail(TileOut o, const int* __restrict__ tile_off, int npanels, unsigned nnz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= npanels) o.tileRowPtr[i] = (unsigned)tile_off[i];
+  if (i == 0) o.tileNnz[tile_off[npanels]] = nnz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SpMM over a panel-ordered nz stream with shared-memory accumulators (tile + seg formats)
+// ---------------------------------------------------------------------------------------------
+// MODE 0: tile format  (tileRowPtr/tileNnz/tileColIdx/rcOffset/newVals)
+// MODE 1: seg format   (per panel: segments seg_off[p]..seg_off[p+1], stream segNzRCIdx/segVals)
+struct AccArgs {
+  const unsigned *tileRowPtr, *tileNnz, *tileColIdx;
+  const int* rcOffset;
+  const float* vals;
+  const int* seg_off;
+  const unsigned *segPtr, *segNzRCIdx;
+  const int* vo_mp;  // output row = vo_mp ? vo_mp[row] : row   (C in ORIGINAL vertex order, flex.cu:994)
+  const float* B;
+  float* C;
+  int m, npanels, k, tm;
+};
+
+template <int KC, int MODE>
+__global__ void __launch_bounds__(256) k_spmm_panel_acc(AccArgs a) {
+  constexpr int LPR = KC / 4, RPW = 32 / LPR, NWK = 8 * RPW;
+  extern __shared__ __align__(16) float sacc[];  // [NWK][tm][KC]
+  auto tile = cg::tiled_partition<LPR>(cg::this_thread_block());
+  const int sl = tile.thread_rank();
+  const int wk = (threadIdx.x >> 5) * RPW + (threadIdx.x & 31) / LPR;
+  const int p = blockIdx.x * NWK + wk;
+  const int kc0 = blockIdx.y * KC;
+  const unsigned k4 = a.k / 4;
+  const bool col_ok = kc0 / 4 + sl < (int)k4;
+  const int c4 = col_ok ? kc0 / 4 + sl : 0;
+  if (p >= a.npanels) return;
+  float4* acc = reinterpret_cast<float4*>(sacc + (size_t)wk * a.tm * KC) + sl;  // row r at acc[r*LPR]
+  for (int r = 0; r < a.tm; ++r) acc[r * LPR] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* B4 = reinterpret_cast<const float4*>(a.B) + c4;
+  unsigned lo, hi;
+  if (MODE == 0) { lo = a.tileNnz[a.tileRowPtr[p]]; hi = a.tileNnz[a.tileRowPtr[p + 1]]; }
+  else { lo = a.segPtr[a.seg_off[p]]; hi = a.segPtr[a.seg_off[p + 1]]; }
+  unsigned tcur = MODE == 0 ? a.tileRowPtr[p] : 0;
+  unsigned last_col = NOCOL;
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (unsigned e0 = lo; e0 < hi; e0 += LPR) {
+    const unsigned e = e0 + sl;
+    int r = 0; unsigned c = 0; float v = 0.f;
+    if (e < hi) {
+      v = a.vals[e];
+      if (MODE == 0) {
+        const int rc = a.rcOffset[e];
+        unsigned t = tcur;
+        while (a.tileNnz[t + 1] <= e) ++t;  // tiles are short: a few steps at most
+        r = rc >> 16;
+        c = a.tileColIdx[t] + (unsigned)(rc & 0xffff);
+      } else {
+        r = (int)a.segNzRCIdx[2 * (size_t)e];
+        c = a.segNzRCIdx[2 * (size_t)e + 1];
+      }
+    }
+    if (MODE == 0) {  // advance the shared tile cursor to the chunk's last entry
+      const unsigned elast = min(e0 + LPR, hi) - 1;
+      while (a.tileNnz[tcur + 1] <= elast) ++tcur;
+    }
+    const int cnt = (int)min((unsigned)LPR, hi - e0);
+    for (int j = 0; j < cnt; ++j) {
+      const unsigned cc = tile.shfl(c, j);
+      const int rr = tile.shfl(r, j);
+      const float vv = tile.shfl(v, j);
+      if (cc != last_col) { b = __ldg(B4 + (size_t)cc * k4); last_col = cc; }  // column-major order: reuse the B row
+      float4 x = acc[rr * LPR];
+      x.x = fmaf(vv, b.x, x.x); x.y = fmaf(vv, b.y, x.y); x.z = fmaf(vv, b.z, x.z); x.w = fmaf(vv, b.w, x.w);
+      acc[rr * LPR] = x;
+    }
+  }
+  if (col_ok)
+    for (int r = 0; r < a.tm; ++r) {
+      const int row = p * a.tm + r;
+      if (row < a.m) {
+        const int orow = a.vo_mp ? a.vo_mp[row] : row;
+        reinterpret_cast<float4*>(a.C)[(size_t)orow * k4 + c4] = acc[r * LPR];
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pillar format kernel (alpha_w_atomic_spmm_v36 semantics)
+// ---------------------------------------------------------------------------------------------
+struct AlphaArgs {
+  const unsigned *alpha_rowPtr, *alpha_colIdx, *pillar_rowPtr, *pillarIdx, *segVoMap;
+  const float* alpha_vals;
+  unsigned* counter;  // n_sm+1, zeroed before every launch (flex.cu:5058)
+  const float* B;
+  float* C;
+  int n_sm, k;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(256) k_spmm_alpha(AlphaArgs a) {
+  constexpr int LPR = KC / 4, RPW = 32 / LPR;
+  auto tile = cg::tiled_partition<LPR>(cg::this_thread_block());
+  const int sl = tile.thread_rank();
+  const int lane = threadIdx.x & 31, sub = lane / LPR;
+  const int kc0 = blockIdx.y * KC;
+  const unsigned k4 = a.k / 4;
+  const bool col_ok = kc0 / 4 + sl < (int)k4;
+  const int c4 = col_ok ? kc0 / 4 + sl : 0;
+  const float4* B4 = reinterpret_cast<const float4*>(a.B) + c4;
+  unsigned smid;
+  asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  const int q_own = (int)(smid % (unsigned)a.n_sm);
+  // a warp pops one pillar at a time: first from its SM's own queue, then from the shared balance queue
+  for (int phase = 0; phase < 2; ++phase) {
+    const int q = phase == 0 ? q_own : a.n_sm;
+    const unsigned qbeg = a.pillarIdx[q], qend = a.pillarIdx[q + 1];
+    while (true) {
+      unsigned pil = 0;
+      if (lane == 0) pil = qbeg + atomicAdd(&a.counter[q * gridDim.y + blockIdx.y], 1u);
+      pil = __shfl_sync(0xffffffffu, pil, 0);
+      if (pil >= qend) break;
+      const unsigned r0 = a.pillar_rowPtr[pil], r1 = a.pillar_rowPtr[pil + 1];
+      for (unsigned rb = r0; rb < r1; rb += RPW) {
+        const unsigned r = rb + sub;
+        const bool act = r < r1;
+        const unsigned lo = act ? a.alpha_rowPtr[r] : 0, hi = act ? a.alpha_rowPtr[r + 1] : 0;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (unsigned e0 = lo; e0 < hi; e0 += LPR) {
+          const unsigned e = e0 + sl;
+          unsigned off = 0; float v = 0.f;
+          if (e < hi) { off = a.alpha_colIdx[e] * k4; v = a.alpha_vals[e]; }
+          const int cnt = (int)min((unsigned)LPR, hi - e0);
+          for (int j = 0; j < cnt; ++j) {
+            const unsigned o = tile.shfl(off, j);
+            const float vv = tile.shfl(v, j);
+            const float4 b = __ldg(B4 + o);
+            acc.x = fmaf(vv, b.x, acc.x); acc.y = fmaf(vv, b.y, acc.y); acc.z = fmaf(vv, b.z, acc.z); acc.w = fmaf(vv, b.w, acc.w);
+          }
+        }
+        if (act && col_ok) {
+          const unsigned vm = a.segVoMap[r];
+          float* dst = a.C + (size_t)(vm & 0x7fffffffu) * a.k + (size_t)c4 * 4;
+          if (vm & 0x80000000u) {  // the row has nz in other pillars too: accumulate (flex.cu:4108-4118)
+            if (hi > lo) { atomicAdd(dst, acc.x); atomicAdd(dst + 1, acc.y); atomicAdd(dst + 2, acc.z); atomicAdd(dst + 3, acc.w); }
+          } else {
+            *reinterpret_cast<float4*>(dst) = acc;
+          }
+        }
+      }
+    }
+  }
+}
+
+int pick_kc(int k) { return k <= 32 ? 32 : (k <= 64 ? 64 : 128); }
+
+template <class T>
+int d2h(std::vector<T>& dst, const void* src, size_t count) {
+  dst.resize(count);
+  if (count) FX_CUDA(cudaMemcpy(dst.data(), src, sizeof(T) * count, cudaMemcpyDeviceToHost));
+  return FX_OK;
+}
+
+}  // namespace
+
+namespace fx {
+
+// ---- host round 1+2 of csr2_DiagTiling and the F4 buckets live in fx_flex_host.cu ----
+int diag_tiling_host(const fx_matrix* m, int tm, int n_sm, fx_flex_dev::PillarHost& out);
+
+static int n_sm_of(const fx_tiles* t) {
+  if (t->opts.n_sm > 0) return t->opts.n_sm;
+  int dev = 0, sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+  return sm;
+}
+
+int flex_carve(fx_tiles* t) {
+  fx_flex_dev& f = t->flex;
+  const fx_matrix* m = t->mat;
+  const int64_t n = m->n, nnz = m->nnz;
+  f.tm = t->opts.tm > 0 ? t->opts.tm : 4;
+  f.tn = t->opts.tn > 0 ? t->opts.tn : 4;
+  f.cmajor = t->opts.cmajor;
+  f.nnz_limit = t->opts.nnz_limit > 0 ? t->opts.nnz_limit : 128;
+  f.n_sm = n_sm_of(t);
+  f.m = (int)n; f.nnz = (int)nnz;
+  f.npanels = (int)((n + f.tm - 1) / f.tm);
+  FX_REQUIRE(f.tm == 2 || f.tm == 4 || f.tm == 8 || f.tm == 16, FX_ERR_ARG, "tm must be 2, 4, 8 or 16 (tileConfs, flex.cu:4146-4152)");
+  FX_REQUIRE(t->format != FX_FMT_TILE || (f.tn >= 1 && f.tn <= 32), FX_ERR_ARG, "tn must be in [1,32] (bitMap is 32 bits)");
+  FX_REQUIRE(t->row_begin == 0 && t->row_end == n, FX_ERR_UNSUPPORTED, "Flex formats are built for the whole matrix");
+  // the reference asserts that no row is empty (mat.cu:1207, :1359)
+  for (int64_t r = 0; r < n; ++r)
+    FX_REQUIRE(m->rowptr[r] < m->rowptr[r + 1], FX_ERR_FORMAT, "row %lld is empty: the Flex builders need every row non-empty (mat.cu:1207,1359)", (long long)r);
+  size_t bytes = 0;
+  auto add = [&](size_t b) { bytes += Arena::pad(b) + 256; };
+  add(sizeof(int) * (f.npanels + 2) * 2);
+  if (t->format == FX_FMT_TILE) {
+    for (int i = 0; i < 4; ++i) add(sizeof(int) * (nnz + 2));  // tileNnz, tileColIdx, nnzTile, bitMap (<= nnz tiles)
+    add(sizeof(int) * (nnz + 2)); add(sizeof(float) * (nnz + 2)); add(sizeof(int) * (f.npanels + 2));
+  } else if (t->format == FX_FMT_SEG) {
+    // segments: every cut but the last of a panel holds >= 116 nz  =>  nsegs <= nnz/116 + npanels
+    f.seg_cap = (int)(nnz / (f.nnz_limit - (int)(0.1 * f.nnz_limit) ) + f.npanels + 2);
+    const size_t rows_cap = (size_t)f.seg_cap * f.tm + 2;
+    add(sizeof(int) * rows_cap * 2);          // alpha_rowPtr, segVoMap
+    add(sizeof(int) * (nnz + 2)); add(sizeof(float) * (nnz + 2));  // alpha_colIdx, alpha_vals
+    add(sizeof(int) * (f.seg_cap + 2) * 2);   // pillar_rowPtr, segPtr
+    add(sizeof(int) * 2 * (nnz + 2)); add(sizeof(float) * (nnz + 2)); add(sizeof(float) * 2 * (nnz + 2));
+    add(sizeof(int) * rows_cap); add(sizeof(int) * ((size_t)f.seg_cap * (f.tm + 1) + 2));
+    add(sizeof(int) * (f.n_sm + 2) * 2);
+  }
+  int rc = t->arena.reserve(bytes + 1024);
+  if (rc != FX_OK) return rc;
+  Arena& A = t->arena;
+  f.count = A.take<int>(f.npanels + 2);
+  f.off = A.take<int>(f.npanels + 2);
+  if (t->format == FX_FMT_TILE) {
+    f.tileNnz = A.take<unsigned>(nnz + 2); f.tileColIdx = A.take<unsigned>(nnz + 2);
+    f.nnzTile = A.take<int>(nnz + 2); f.bitMap = A.take<int>(nnz + 2);
+    f.rcOffset = A.take<int>(nnz + 2); f.newVals = A.take<float>(nnz + 2);
+    f.tileRowPtr = A.take<unsigned>(f.npanels + 2);
+    if (!f.tileRowPtr) { set_error("arena overflow"); return FX_ERR_NOMEM; }
+  } else if (t->format == FX_FMT_SEG) {
+    const size_t rows_cap = (size_t)f.seg_cap * f.tm + 2;
+    f.alpha_rowPtr = A.take<unsigned>(rows_cap); f.segVoMap = A.take<unsigned>(rows_cap);
+    f.alpha_colIdx = A.take<unsigned>(nnz + 2); f.alpha_vals = A.take<float>(nnz + 2);
+    f.pillar_rowPtr = A.take<unsigned>(f.seg_cap + 2); f.segPtr = A.take<unsigned>(f.seg_cap + 2);
+    f.segNzRCIdx = A.take<unsigned>(2 * (nnz + 2)); f.segVals = A.take<float>(nnz + 2);
+    f.segNzCV = A.take<float>(2 * (nnz + 2));
+    f.segVoMapPad = A.take<unsigned>(rows_cap); f.seg_rowPtr = A.take<int>((size_t)f.seg_cap * (f.tm + 1) + 2);
+    f.next_seg = A.take<int>(f.n_sm + 2); f.grouped_tailSeg = A.take<int>(f.n_sm + 2);
+    if (!f.grouped_tailSeg) { set_error("arena overflow"); return FX_ERR_NOMEM; }
+  }
+  return FX_OK;
+}
+
+template <bool WRITE>
+static int launch_seg(const fx_tiles* t, cudaStream_t s, SegOut o) {
+  const fx_flex_dev& f = t->flex;
+  const fx_matrix* m = t->mat;
+  const int threads = 128;
+  const int grid = ceil_div((long long)f.npanels * f.tm, threads);
+#define FX_SEG(TM) k_seg<TM, WRITE><<<grid, threads, 0, s>>>(m->rowptr_dev, m->col_dev, m->val_dev, m->vo_mp_dev, f.m, f.npanels, f.nnz_limit, f.count, f.off, o)
+  switch (f.tm) { case 2: FX_SEG(2); break; case 4: FX_SEG(4); break; case 8: FX_SEG(8); break; default: FX_SEG(16); }
+#undef FX_SEG
+  FX_LAUNCH_CHECK();
+  return FX_OK;
+}
+
+template <bool WRITE>
+static int launch_tile(const fx_tiles* t, cudaStream_t s, TileOut o) {
+  const fx_flex_dev& f = t->flex;
+  const fx_matrix* m = t->mat;
+  const int threads = 128;
+  const int grid = ceil_div((long long)f.npanels * f.tm, threads);
+#define FX_TILE(TM) k_tile<TM, WRITE><<<grid, threads, 0, s>>>(m->rowptr_dev, m->col_dev, m->val_dev, f.m, f.m, f.npanels, f.tn, f.cmajor, f.count, f.off, o)
+  switch (f.tm) { case 2: FX_TILE(2); break; case 4: FX_TILE(4); break; case 8: FX_TILE(8); break; default: FX_TILE(16); }
+#undef FX_TILE
+  FX_LAUNCH_CHECK();
+  return FX_OK;
+}
+
+int flex_build(fx_tiles* t, cudaStream_t s) {
+  fx_flex_dev& f = t->flex;
+  if (t->format == FX_FMT_SEG) {
+    SegOut o{f.alpha_rowPtr, f.alpha_colIdx, f.pillar_rowPtr, f.segVoMap, f.alpha_vals, f.segPtr, f.segNzRCIdx,
+             f.segVoMapPad, f.segVals, f.segNzCV, f.seg_rowPtr};
+    int rc = launch_seg<false>(t, s, o);
+    if (rc) return rc;
+    k_scan_int<<<1, 1024, 0, s>>>(f.count, f.npanels, f.off);
+    FX_LAUNCH_CHECK();
+    rc = launch_seg<true>(t, s, o);
+    if (rc) return rc;
+    // totals + the per-panel counts come to the host: the F4 bucket walk is a 149-step greedy
+    f.h_count.resize(f.npanels);
+    FX_CUDA(cudaMemcpyAsync(t->stats_host, f.off + f.npanels, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaMemcpyAsync(f.h_count.data(), f.count, sizeof(int) * f.npanels, cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaStreamSynchronize(s));
+    f.nsegs = *reinterpret_cast<int*>(t->stats_host);
+    const int last_rows = f.m - (f.npanels - 1) * f.tm;
+    f.rows_total = f.nsegs * f.tm - (f.npanels ? f.h_count[f.npanels - 1] * (f.tm - last_rows) : 0);
+    k_seg_tail<<<1, 1, 0, s>>>(o, f.nsegs, f.rows_total, (unsigned)f.nnz);
+    FX_LAUNCH_CHECK();
+    // F4 (mat.cu:1118-1162, row_based_split)
+    f.h_next.assign(f.n_sm + 1, 0); f.h_tail.assign(f.n_sm + 1, 0);
+    {
+      const int segload = f.nsegs / f.n_sm;
+      int head = 0, tail = 0, panel = 0;
+      for (int i = 0; i < f.n_sm; ++i) {
+        f.h_next[i] = head;
+        if (panel < f.npanels) {
+          int cur = f.h_count[panel];
+          tail = head + cur;
+          while (++panel < f.npanels) {
+            if (f.h_count[panel] + cur > segload) break;
+            cur += f.h_count[panel];
+            tail += f.h_count[panel];
+          }
+        }
+        f.h_tail[i] = std::min(f.nsegs, tail);
+        head = std::min(f.nsegs, tail);
+      }
+      f.h_next[f.n_sm] = head;
+      f.h_tail[f.n_sm] = f.nsegs;
+    }
+    FX_CUDA(cudaMemcpyAsync(f.next_seg, f.h_next.data(), sizeof(int) * (f.n_sm + 1), cudaMemcpyHostToDevice, s));
+    FX_CUDA(cudaMemcpyAsync(f.grouped_tailSeg, f.h_tail.data(), sizeof(int) * (f.n_sm + 1), cudaMemcpyHostToDevice, s));
+    return FX_OK;
+  }
+  if (t->format == FX_FMT_TILE) {
+    TileOut o{f.tileRowPtr, f.tileNnz, f.tileColIdx, f.nnzTile, f.bitMap, f.rcOffset, f.newVals};
+    int rc = launch_tile<false>(t, s, o);
+    if (rc) return rc;
+    k_scan_int<<<1, 1024, 0, s>>>(f.count, f.npanels, f.off);
+    FX_LAUNCH_CHECK();
+    rc = launch_tile<true>(t, s, o);
+    if (rc) return rc;
+    k_tile_tail<<<ceil_div(f.npanels + 1, 256), 256, 0, s>>>(o, f.off, f.npanels, (unsigned)f.nnz);
+    FX_LAUNCH_CHECK();
+    FX_CUDA(cudaMemcpyAsync(t->stats_host, f.off + f.npanels, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaStreamSynchronize(s));
+    f.ntiles = *reinterpret_cast<int*>(t->stats_host);
+    return FX_OK;
+  }
+  if (t->format == FX_FMT_PILLAR) {
+    // Round 1 of csr2_DiagTiling grows the diagonal blocks one row at a time, each block starting
+    // where the previous one ended (mat.cu:706-759): a serial dependence over the whole diagonal, so
+    // -- like the reference -- this format is built on the host and uploaded (it is inside tPre).
+    int rc = diag_tiling_host(t->mat, f.tm, f.n_sm, f.ph);
+    if (rc) return rc;
+    auto& P = f.ph;
+    f.rows_total = (int)P.alpha_rowPtr.size() - 1;
+    f.nsegs = P.n_segs;
+    auto up = [&](auto*& dptr, const auto& v) -> int {
+      using T = typename std::remove_reference<decltype(v)>::type::value_type;
+      if (dptr) cudaFree(dptr);
+      dptr = nullptr;
+      FX_CUDA(cudaMalloc(&dptr, sizeof(T) * std::max<size_t>(v.size(), 1)));
+      FX_CUDA(cudaMemcpyAsync(dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, s));
+      return FX_OK;
+    };
+    if ((rc = up(f.alpha_rowPtr, P.alpha_rowPtr)) || (rc = up(f.alpha_colIdx, P.alpha_colIdx)) ||
+        (rc = up(f.alpha_vals, P.alpha_vals)) || (rc = up(f.pillar_rowPtr, P.alpha_pillar_rowPtr)) ||
+        (rc = up(f.pillarIdx, P.alpha_pillarIdx)) || (rc = up(f.segVoMap, P.segVoMap)))
+      return rc;
+    if (f.counter) cudaFree(f.counter);
+    FX_CUDA(cudaMalloc(&f.counter, sizeof(unsigned) * (f.n_sm + 1) * 16));
+    f.pillar_owned = true;
+    return FX_OK;
+  }
+  set_error("flex_build: unknown format");
+  return FX_ERR_ARG;
+}
+
+int flex_spmm(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s) {
+  const fx_flex_dev& f = t->flex;
+  const fx_matrix* m = t->mat;
+  FX_REQUIRE(k % 4 == 0, FX_ERR_UNSUPPORTED, "Flex-format kernels need k %% 4 == 0 (vec4 kernels, SURVEY 8b)");
+  const int KC = pick_kc(k);
+  const int kchunks = ceil_div(k, KC);
+  if (t->format == FX_FMT_PILLAR) {
+    AlphaArgs a{f.alpha_rowPtr, f.alpha_colIdx, f.pillar_rowPtr, f.pillarIdx, f.segVoMap, f.alpha_vals, f.counter, B, C, f.n_sm, k};
+    FX_REQUIRE(kchunks <= 16, FX_ERR_UNSUPPORTED, "k too large for the pillar kernel's counters");
+    FX_CUDA(cudaMemsetAsync(f.counter, 0, sizeof(unsigned) * (f.n_sm + 1) * kchunks, s));  // flex.cu:5058
+    FX_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)f.m * k, s));                    // flex.cu:5057 (atomics)
+    dim3 grid(f.n_sm * 8, kchunks);
+    if (KC == 32) k_spmm_alpha<32><<<grid, 256, 0, s>>>(a);
+    else if (KC == 64) k_spmm_alpha<64><<<grid, 256, 0, s>>>(a);
+    else k_spmm_alpha<128><<<grid, 256, 0, s>>>(a);
+    FX_LAUNCH_CHECK();
+    return FX_OK;
+  }
+  AccArgs a{};
+  a.B = B; a.C = C; a.m = f.m; a.npanels = f.npanels; a.k = k; a.tm = f.tm;
+  a.vo_mp = m->info.order != FX_ORDER_OVO ? m->vo_mp_dev : nullptr;
+  const int RPW = 32 / (KC / 4), NWK = 8 * RPW;
+  const size_t smem = (size_t)NWK * f.tm * KC * sizeof(float);
+  dim3 grid(ceil_div(f.npanels, NWK), kchunks);
+#define FX_ACC(KCV, MODE)                                                                                       \
+  do {                                                                                                          \
+    if (smem > 48 * 1024)                                                                                       \
+      FX_CUDA(cudaFuncSetAttribute(k_spmm_panel_acc<KCV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_spmm_panel_acc<KCV, MODE><<<grid, 256, smem, s>>>(a);                                                     \
+  } while (0)
+  if (t->format == FX_FMT_TILE) {
+    a.tileRowPtr = f.tileRowPtr; a.tileNnz = f.tileNnz; a.tileColIdx = f.tileColIdx; a.rcOffset = f.rcOffset; a.vals = f.newVals;
+    if (KC == 32) FX_ACC(32, 0); else if (KC == 64) FX_ACC(64, 0); else FX_ACC(128, 0);
+  } else {
+    a.seg_off = f.off; a.segPtr = f.segPtr; a.segNzRCIdx = f.segNzRCIdx; a.vals = f.segVals;
+    if (KC == 32) FX_ACC(32, 1); else if (KC == 64) FX_ACC(64, 1); else FX_ACC(128, 1);
+  }
+#undef FX_ACC
+  FX_LAUNCH_CHECK();
+  return FX_OK;
+}
+
+void flex_release(fx_tiles* t) {
+  fx_flex_dev& f = t->flex;
+  if (f.pillar_owned) {
+    cudaFree(f.alpha_rowPtr); cudaFree(f.alpha_colIdx); cudaFree(f.alpha_vals); cudaFree(f.pillar_rowPtr);
+    cudaFree(f.pillarIdx); cudaFree(f.segVoMap); cudaFree(f.counter);
+  }
+}
+
+}  // namespace fx
+
+extern "C" int fx_tiles_export_tile(fx_tiles* t, fx_tile_arrays* o) {
+  FX_REQUIRE(t && o && t->format == FX_FMT_TILE, FX_ERR_ARG, "fx_tiles_export_tile: not a tile-format handle");
+  fx_flex_dev& f = t->flex;
+  FX_CUDA(cudaDeviceSynchronize());
+  int rc;
+  if ((rc = d2h(f.e_u32[0], f.tileRowPtr, f.npanels + 1)) || (rc = d2h(f.e_u32[1], f.tileNnz, f.ntiles + 1)) ||
+      (rc = d2h(f.e_i32[0], f.nnzTile, f.ntiles)) || (rc = d2h(f.e_i32[1], f.bitMap, f.ntiles)) ||
+      (rc = d2h(f.e_u32[2], f.tileColIdx, f.ntiles)) || (rc = d2h(f.e_i32[2], f.rcOffset, f.nnz)) ||
+      (rc = d2h(f.e_f32[0], f.newVals, f.nnz)))
+    return rc;
+  o->m = f.m; o->tm = f.tm; o->tn = f.tn; o->ntiles = f.ntiles; o->npanels = f.npanels; o->nnz = f.nnz; o->cmajor = f.cmajor;
+  o->tileRowPtr = f.e_u32[0].data(); o->tileNnz = f.e_u32[1].data(); o->nnzTile = f.e_i32[0].data();
+  o->bitMap = f.e_i32[1].data(); o->tileColIdx = f.e_u32[2].data(); o->rcOffset = f.e_i32[2].data();
+  o->newVals = f.e_f32[0].data();
+  return FX_OK;
+}
+
+extern "C" int fx_tiles_export_seg(fx_tiles* t, fx_seg_arrays* o) {
+  FX_REQUIRE(t && o && t->format == FX_FMT_SEG, FX_ERR_ARG, "fx_tiles_export_seg: not a seg-format handle");
+  fx_flex_dev& f = t->flex;
+  FX_CUDA(cudaDeviceSynchronize());
+  int rc;
+  const size_t R = f.rows_total, S = f.nsegs, N = f.nnz;
+  if ((rc = d2h(f.e_u32[0], f.alpha_rowPtr, R + 1)) || (rc = d2h(f.e_u32[1], f.alpha_colIdx, N)) ||
+      (rc = d2h(f.e_u32[2], f.pillar_rowPtr, S + 1)) || (rc = d2h(f.e_u32[3], f.segVoMap, R)) ||
+      (rc = d2h(f.e_f32[0], f.alpha_vals, N)) || (rc = d2h(f.e_u32[4], f.segPtr, S + 1)) ||
+      (rc = d2h(f.e_u32[5], f.segNzRCIdx, 2 * N)) || (rc = d2h(f.e_u32[6], f.segVoMapPad, S * f.tm)) ||
+      (rc = d2h(f.e_f32[1], f.segVals, N)) || (rc = d2h(f.e_f32[2], f.segNzCV, 2 * N)) ||
+      (rc = d2h(f.e_i32[0], f.seg_rowPtr, S * (f.tm + 1))))
+    return rc;
+  o->m = f.m; o->tm = f.tm; o->nnz = f.nnz; o->nsegs = f.nsegs; o->rows_total = f.rows_total; o->npanels = f.npanels; o->n_sm = f.n_sm;
+  o->alpha_rowPtr = f.e_u32[0].data(); o->alpha_colIdx = f.e_u32[1].data(); o->alpha_pillar_rowPtr = f.e_u32[2].data();
+  o->segVoMap = f.e_u32[3].data(); o->alpha_vals = f.e_f32[0].data(); o->segs_per_panel = f.h_count.data();
+  o->segPtr = f.e_u32[4].data(); o->segNzRCIdx = f.e_u32[5].data(); o->segVoMapPad = f.e_u32[6].data();
+  o->segVals = f.e_f32[1].data(); o->segNzCV = f.e_f32[2].data(); o->seg_rowPtr = f.e_i32[0].data();
+  o->next_seg = f.h_next.data(); o->grouped_tailSeg = f.h_tail.data();
+  return FX_OK;
+}
+
+extern "C" int fx_tiles_export_pillar(fx_tiles* t, fx_pillar_arrays* o) {
+  FX_REQUIRE(t && o && t->format == FX_FMT_PILLAR, FX_ERR_ARG, "fx_tiles_export_pillar: not a pillar-format handle");
+  fx_flex_dev& f = t->flex;
+  auto& P = f.ph;
+  o->m = f.m; o->nnz = f.nnz; o->n_sm = f.n_sm; o->n_segs = P.n_segs; o->rows_total = f.rows_total;
+  o->warps_with_weights = P.warps_with_weights;
+  o->alpha_rowPtr = P.alpha_rowPtr.data(); o->alpha_colIdx = P.alpha_colIdx.data();
+  o->alpha_pillar_rowPtr = P.alpha_pillar_rowPtr.data(); o->alpha_pillarIdx = P.alpha_pillarIdx.data();
+  o->segVoMap = P.segVoMap.data(); o->alpha_vals = P.alpha_vals.data();
+  o->empty_wp_p = P.empty_wp_p; o->band_nz_p = P.band_nz_p;
+  return FX_OK;
+}

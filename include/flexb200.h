@@ -63,7 +63,8 @@ typedef struct {
   int32_t nnz_limit;  /* NNZ_LIMIT (mat.cuh:16), 0 = 128 */
   int32_t n_sm;       /* SM count for F4/F5 bucketing, 0 = device value */
   int32_t row_begin, row_end; /* build only rows [row_begin,row_end) (row-panel shard); 0,0 = all */
-  int32_t reserved[8];
+  int32_t cmajor;     /* FX_FMT_TILE: 0 = csr2flex_Rmajor, 1 = csr2flex_Cmajor (COL_MAJ_TILE, DataLoader.cuh:18) */
+  int32_t reserved[7];
 } fx_build_opts;
 
 typedef struct { /* ASpT metadata export for bit-exact checks; pointers are host copies
@@ -75,6 +76,34 @@ typedef struct { /* ASpT metadata export for bit-exact checks; pointers are host
   const int32_t *perm, *csr_e, *special, *special2;
   const float *csr_ev;
 } fx_aspt_arrays;
+
+typedef struct { /* Flex tile format (mat.cu:1345-1518; Mat_POD fields mat.cuh:27-34), host copies */
+  int32_t m, tm, tn, ntiles, npanels, nnz, cmajor;
+  const uint32_t *tileRowPtr; /* npanels+1 */
+  const uint32_t *tileNnz;    /* ntiles+1 */
+  const int32_t *nnzTile, *bitMap; /* ntiles */
+  const uint32_t *tileColIdx; /* ntiles */
+  const int32_t *rcOffset;    /* nnz: (rowInPanel<<16)|(col-tileColIdx) */
+  const float *newVals;       /* nnz */
+} fx_tile_arrays;
+
+typedef struct { /* row-panel segmentation (mat.cu:1192-1269) + SM buckets (mat.cu:1118-1162), host copies */
+  int32_t m, tm, nnz, nsegs, rows_total, npanels, n_sm;
+  const uint32_t *alpha_rowPtr, *alpha_colIdx, *alpha_pillar_rowPtr, *segVoMap;
+  const float *alpha_vals;
+  const int32_t *segs_per_panel;
+  const uint32_t *segPtr, *segNzRCIdx, *segVoMapPad; /* tile-segment arrays of kernels v10-v35 */
+  const float *segVals, *segNzCV;
+  const int32_t *seg_rowPtr;
+  const int32_t *next_seg, *grouped_tailSeg; /* n_sm+1 each */
+} fx_seg_arrays;
+
+typedef struct { /* diagonal tiling / pillar format (mat.cu:680-903; Mat_POD mat.cuh:49-55), host copies */
+  int32_t m, nnz, n_sm, n_segs, rows_total, warps_with_weights;
+  const uint32_t *alpha_rowPtr, *alpha_colIdx, *alpha_pillar_rowPtr, *alpha_pillarIdx, *segVoMap;
+  const float *alpha_vals;
+  float empty_wp_p, band_nz_p;
+} fx_pillar_arrays;
 
 typedef struct { /* what run()/process() print: flex.cu:5134-5631, aspt/sspmm_128.cu:1406-1446 */
   float tPre_ms, tElap_ms;
@@ -132,6 +161,9 @@ int fx_build(const fx_matrix *m, const fx_build_opts *opts, fx_tiles **out, floa
 /* repeat the build into the same arena (timing loops) */
 int fx_rebuild(fx_tiles *t, float *tPre_ms);
 int fx_tiles_export_aspt(fx_tiles *t, fx_aspt_arrays *out);
+int fx_tiles_export_tile(fx_tiles *t, fx_tile_arrays *out);
+int fx_tiles_export_seg(fx_tiles *t, fx_seg_arrays *out);
+int fx_tiles_export_pillar(fx_tiles *t, fx_pillar_arrays *out);
 void fx_tiles_free(fx_tiles *t); /* Mat::freeMatGPU* mat.cuh:184-220 */
 
 /* ---- L3: SpMM ---------------------------------------------------------------------- */
