@@ -64,21 +64,6 @@ def load_workload(name, k, device, shuffle=False):
     return synth.generate(name, device=device, shuffle=shuffle)
 
 
-def panel_shards(rowptr_host, n, world):
-    """nnz-balanced contiguous row ranges aligned to the 128-row panel height."""
-    import numpy as np
-    npanel = (n + 127) // 128
-    pstart = np.minimum(np.arange(npanel + 1) * 128, n)
-    pnnz = rowptr_host[pstart]
-    total = int(pnnz[-1])
-    cuts = [0]
-    for r in range(1, world):
-        cuts.append(int(np.searchsorted(pnnz, total * r / world)))
-    cuts.append(npanel)
-    cuts = np.maximum.accumulate(np.array(cuts))
-    return [(int(pstart[cuts[r]]), int(pstart[cuts[r + 1]])) for r in range(world)]
-
-
 class ClockSampler(threading.Thread):
     """NVML clocks / throttle reasons every few ms while the timed region runs."""
 
@@ -245,7 +230,8 @@ def main():
         rp_host = dl.rowPtr.astype(np.int64)
     else:
         dl = fx.DataLoader.from_device(n, nnz, rp32.data_ptr(), c32.data_ptr(), v.data_ptr(), k, args.workload + ".csv")
-    shards = panel_shards(rp_host, n, world)
+    from flex_b200.shard import panel_shards
+    shards = panel_shards(rp_host, world)
     lo, hi = shards[rank]
     mat = fx.Mat(dl, fmt=args.fmt, row_begin=lo, row_end=hi)
     tpre = [mat.tPre_ms] + [mat.rebuild() for _ in range(3)]
@@ -321,13 +307,12 @@ def main():
 
     ag_ms = None
     if args.allgather and dist is not None:
-        rows = [s[1] - s[0] for s in shards]
-        outs = [torch.empty((r, k), dtype=torch.float32, device=dev) for r in rows]
-        dist.all_gather(outs, Cd)  # warm-up
+        from flex_b200.shard import gather_rows
+        gather_rows(dist, Cd, shards, k)  # warm-up
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
-        dist.all_gather(outs, Cd)
+        gather_rows(dist, Cd, shards, k)
         a1.record()
         a1.synchronize()
         ag = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)

@@ -45,17 +45,20 @@ def small_graph(n, deg, seed, sym):
 
 def reference(cmd, name, path, *args):
     """flexref output, live if available, else the committed golden fixture."""
-    if ref.available():
+    if ref.available() and not os.environ.get("FLEX_NO_FLEXREF"):
         return ref.run(cmd, path, *args)
     f = os.path.join(GOLDEN, f"{name}_{cmd}_{'_'.join(map(str, args))}.npz")
     if not os.path.exists(f):
-        pytest.skip(f"no flexref and no fixture {os.path.basename(f)}")
-    return dict(np.load(f))
+        return None  # e.g. pubmed's large dumps are not stored: that graph is pinned only with flexref
+    d = dict(np.load(f))
+    return {k: (v.item() if v.ndim == 0 else v) for k, v in d.items()}
 
 
 def test_loader_pinned(orc, tmp_path):
     for name, path in graphs(tmp_path):
         r = reference("load", name, path)
+        if r is None:
+            continue
         m = orc.csv_load(path)
         dl = fx.DataLoader(path, 4)
         rp, c, v = dl.host_csr()
@@ -79,9 +82,18 @@ def test_orderings_pinned(orc, tmp_path, kind):
     tag = {"deg": fx.FX_ORDER_DEG, "rcm": fx.FX_ORDER_RCM, "gor": fx.FX_ORDER_GOR}[kind]
     for name, path in graphs(tmp_path):
         m = orc.csv_load(path)
-        rk = reference("rank", name, path, kind)["rank"].astype(np.uint64)
+        rk = reference("rank", name, path, kind)
+        if rk is None:
+            continue
+        rk = rk["rank"].astype(np.uint64)
         assert np.array_equal(orc.order(kind, m["rowptr"], m["col"]), rk), (name, kind, "oracle rank")
+        d1 = fx.DataLoader(path, 4).reorder(tag)
+        inv = np.empty(m["n"], np.int64)
+        inv[rk.astype(np.int64)] = np.arange(m["n"])
+        assert np.array_equal(d1.vo_mp, inv), (name, kind, "product rank")
         r = reference("order", name, path, kind)
+        if r is None:
+            continue
         vo, rp2, c2, v2 = orc.perm_apply(m["rowptr"], m["col"], m["val"], rk)
         assert np.array_equal(r["vo_mp"], vo) and np.array_equal(r["rowPtr"], rp2)
         assert np.array_equal(r["col"], c2) and np.array_equal(r["vals"], v2)
@@ -98,6 +110,8 @@ def test_seg_pinned(orc, tmp_path, tm):
     for name, path in graphs(tmp_path):
         m = orc.csv_load(path)
         r = reference("seg", name, path, tm)
+        if r is None:
+            continue
         s = orc.seg(m["rowptr"], m["col"], m["val"], np.arange(m["n"], dtype=np.int32), tm)
         for f in ("alpha_rowPtr", "alpha_colIdx", "alpha_vals", "alpha_pillar_rowPtr", "segVoMap", "segs_per_panel"):
             assert np.array_equal(r[f], s[f]), (name, tm, f)
@@ -112,6 +126,8 @@ def test_flex_tile_pinned(orc, tmp_path, tmtn, major):
     for name, path in graphs(tmp_path):
         m = orc.csv_load(path)
         r = reference("tile", name, path, tm, tn, major)
+        if r is None:
+            continue
         t = orc.flex_tile(m["rowptr"], m["col"], m["val"], tm, tn, major == "C")
         for f in ("tileRowPtr", "tileNnz", "nnzTile", "bitMap", "tileColIdx", "rcOffset", "newVals"):
             assert np.array_equal(r[f], t[f]), (name, tm, tn, major, f)
@@ -130,10 +146,13 @@ def test_diag_tiling_pinned(orc, tmp_path, n_sm):
                 # a row without its diagonal near the end of the matrix: the reference's walk
                 # (mat.cu:718-727) reads past the end of colIdx -- undefined there, nothing to pin
                 continue
-            with pytest.raises(RuntimeError):  # every other refusal mirrors a reference assert
-                reference("diag", name, path, 4, n_sm)
+            if ref.available() and not os.environ.get("FLEX_NO_FLEXREF"):
+                with pytest.raises(RuntimeError):  # every other refusal mirrors a reference assert
+                    reference("diag", name, path, 4, n_sm)
             continue
         r = reference("diag", name, path, 4, n_sm)
+        if r is None:
+            continue
         for f in ("alpha_rowPtr", "alpha_colIdx", "alpha_vals", "alpha_pillar_rowPtr", "alpha_pillarIdx", "segVoMap"):
             assert np.array_equal(r[f], d[f]), (name, n_sm, f)
         assert int(r["n_segs"]) == d["n_segs"]
