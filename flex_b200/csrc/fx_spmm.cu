@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special(PanelArgs a, 
 // TILES=false: panels without a dense tile -- no dynamic shared memory, the SM keeps its L1.
 // TILES=true : the first TS dense tiles of the panel are TMA-staged in shared memory; nz of those
 //              tiles read B from there, all other nz (further tiles, sparse tail) from L1/L2.
-template <int KC, int WARPS, bool TILES>
-__global__ void __launch_bounds__(WARPS * 32) k_spmm_panel(PanelArgs a, const int* __restrict__ plist) {
+template <int KC, int WARPS, bool TILES, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_panel(PanelArgs a, const int* __restrict__ plist) {
   constexpr int LPR = KC / 4, RPW = 32 / LPR, NW = WARPS * RPW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // dynamic shared memory: [TILES: TS*BW*KC floats] [part: 2*NW*KC floats] [sbuf: NW*2*LPR uint2]
@@ -460,30 +460,45 @@ static int panel_warps() {
   return w;
 }
 
-template <int KC, int WARPS>
+template <int KC, int WARPS, int MINB>
 static int launch_panels(const fx_aspt_dev& d, const PanelArgs& a, int kchunks, cudaStream_t s) {
+  // Shared-memory staging of dense tiles only pays when a large share of the nz sits in them: the
+  // tile memory (64 KB per tile at k=128) comes out of the SM's L1, which serves the sparse nz.
+  // Measured on Reddit-shape (6 % of nz in tiles): 0.855 ms with the tiled CTAs, 0.759 ms without.
+  const char* tiles_env = getenv("FLEX_TILES");  // "0" never, "1" always, unset = by density
+  const double dense_frac = d.ne > 0 ? (double)(d.ne - d.S1) / d.ne : 0.0;
+  const bool use_tiles = tiles_env ? atoi(tiles_env) != 0 : dense_frac >= 0.25;
+  if (!use_tiles || d.n_tiled == 0) {  // every panel through the L1 path (dense groups are ordinary nz there)
+    constexpr int NW0 = WARPS * (32 / (KC / 4));
+    const size_t ws = (size_t)2 * NW0 * KC * sizeof(float) + (size_t)NW0 * 2 * (KC / 4) * sizeof(uint2);
+    FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
+    dim3 grid(d.npanel, kchunks);
+    k_spmm_panel<KC, WARPS, false, MINB><<<grid, WARPS * 32, ws, s>>>(a, nullptr);
+    FX_LAUNCH_CHECK();
+    return FX_OK;
+  }
   // per-worker partial slots + (offset,value) staging buffers
   constexpr int NW = WARPS * (32 / (KC / 4));
   const size_t work_smem = (size_t)2 * NW * KC * sizeof(float) + (size_t)NW * 2 * (KC / 4) * sizeof(uint2);
   if (d.n_plain > 0) {
     static bool carve = false;
     if (!carve) {
-      FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)work_smem));
+      FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)work_smem));
       carve = true;
     }
     dim3 grid(d.n_plain, kchunks);
-    k_spmm_panel<KC, WARPS, false><<<grid, WARPS * 32, work_smem, s>>>(a, d.n_tiled ? d.plist_plain : nullptr);
+    k_spmm_panel<KC, WARPS, false, MINB><<<grid, WARPS * 32, work_smem, s>>>(a, d.n_tiled ? d.plist_plain : nullptr);
     FX_LAUNCH_CHECK();
   }
   if (d.n_tiled > 0) {
     const size_t smem = (size_t)a.TS * a.BW * KC * sizeof(float) + work_smem;
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
-      FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set = smem;
     }
     dim3 grid(d.n_tiled, kchunks);
-    k_spmm_panel<KC, WARPS, true><<<grid, WARPS * 32, smem, s>>>(a, d.plist_tiled);
+    k_spmm_panel<KC, WARPS, true, MINB><<<grid, WARPS * 32, smem, s>>>(a, d.plist_tiled);
     FX_LAUNCH_CHECK();
   }
   return FX_OK;
@@ -499,10 +514,11 @@ static int launch_aspt(const fx_tiles* t, const PanelArgs& a, int special_p, cud
     k_spmm_special<KC><<<g, PANEL_WARPS * 32, 0, s>>>(a, d.special, d.special2, special_p, d.partial);
     FX_LAUNCH_CHECK();
   }
+  static int minb = getenv("FLEX_MINB") ? atoi(getenv("FLEX_MINB")) : 3;
   switch (panel_warps()) {
-    case 8: return launch_panels<KC, 8>(d, a, kchunks, s);
-    case 32: return launch_panels<KC, 32>(d, a, kchunks, s);
-    default: return launch_panels<KC, 16>(d, a, kchunks, s);
+    case 8: return minb >= 6 ? launch_panels<KC, 8, 6>(d, a, kchunks, s) : launch_panels<KC, 8, 1>(d, a, kchunks, s);
+    case 32: return launch_panels<KC, 32, 1>(d, a, kchunks, s);
+    default: return minb >= 3 ? launch_panels<KC, 16, 3>(d, a, kchunks, s) : launch_panels<KC, 16, 1>(d, a, kchunks, s);
   }
 }
 
@@ -513,7 +529,9 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   PanelArgs a;
   a.mcsr_cnt = d.mcsr_cnt; a.mcsr_e = d.mcsr_e_use; a.mcsr_list = d.mcsr_list;
   a.csr_e = d.csr_e_use; a.csr_ev = d.csr_ev_use;
-  a.spec_off = d.special_p > 0 ? d.spec_off : nullptr;
+  static const bool no_special = getenv("FLEX_NO_SPECIAL") != nullptr;
+  const int special_p = no_special ? 0 : d.special_p;
+  a.spec_off = special_p > 0 ? d.spec_off : nullptr;
   a.partial = d.partial;
   a.B = B; a.C = C;
   a.npanel = d.npanel; a.nloc = t->row_end - t->row_begin; a.k = k; a.BW = d.BW;
@@ -523,9 +541,9 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   while (ts > 1 && ts * tile_bytes > 160 * 1024) --ts;  // leave room for the per-worker buffers
   a.TS = ts > 0 ? ts : 1;
   if (d.max_tp == 0) a.TS = 0;
-  if (KC == 32) return launch_aspt<32>(t, a, d.special_p, s);
-  if (KC == 64) return launch_aspt<64>(t, a, d.special_p, s);
-  return launch_aspt<128>(t, a, d.special_p, s);
+  if (KC == 32) return launch_aspt<32>(t, a, special_p, s);
+  if (KC == 64) return launch_aspt<64>(t, a, special_p, s);
+  return launch_aspt<128>(t, a, special_p, s);
 }
 
 int permute_rows(const int32_t* map, int64_t n, int k, const float* src, float* dst, bool scatter, cudaStream_t s) {

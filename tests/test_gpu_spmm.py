@@ -64,8 +64,16 @@ def test_reference_fixtures(orc, data_dir, name, k):
         mat.free()
 
 
+@pytest.fixture(params=["1", "0"], ids=["tiles_smem", "tiles_l1"])
+def tile_path(request, monkeypatch):
+    """Both kernel paths for panels with dense tiles: TMA-staged shared memory (FLEX_TILES=1) and the
+    L1 path (FLEX_TILES=0); unset, the library picks by the share of nz in tiles."""
+    monkeypatch.setenv("FLEX_TILES", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("k", [4, 8, 20, 32, 64, 100, 128, 256])
-def test_k_sweep_with_dense_tiles(orc, k):
+def test_k_sweep_with_dense_tiles(orc, k, tile_path):
     n = 1500
     rp, c, v = random_csr(n, 6, 21, hubs=2, blocks=8)
     dl = fx.DataLoader.from_arrays(rp, c, v, k)
@@ -99,7 +107,7 @@ def test_k_not_multiple_of_4(orc, k):
 
 @pytest.mark.parametrize("bw", [128, 256])
 @pytest.mark.parametrize("seed", [1, 2, 3])
-def test_builder_bit_exact(orc, bw, seed):
+def test_builder_bit_exact(orc, bw, seed, tile_path):
     n = 128 * 9 + 37  # ragged last panel
     rp, c, v = random_csr(n, 5 + seed, 100 + seed, hubs=3, blocks=10)
     dl = fx.DataLoader.from_arrays(rp, c, v, 64)
@@ -113,7 +121,7 @@ def test_builder_bit_exact(orc, bw, seed):
     mat.free()
 
 
-def test_many_tiles_per_panel(orc):
+def test_many_tiles_per_panel(orc, tile_path):
     # one panel with several stacked dense tiles (more than fit in shared memory at once)
     n = 2048
     rng = np.random.default_rng(0)
