@@ -345,16 +345,21 @@ def main():
         if ag_ms is not None:
             line["allgather_ms"] = ag_ms
         if args.cusparse:
+            # context only, same protocol as the timed region (L2 flushed between steps when it fits)
             A = torch.sparse_csr_tensor(rp, c, v, size=(n, n))
             for _ in range(3):
                 torch.sparse.mm(A, B)
             torch.cuda.synchronize()
             c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            c0.record()
+            tot = 0.0
             for _ in range(10):
+                if small:
+                    flush.fill_(1.0)
+                c0.record()
                 torch.sparse.mm(A, B)
-            c1.record(); c1.synchronize()
-            line["cusparse_context_gflops"] = flops / (c0.elapsed_time(c1) / 10 * 1e-3) / 1e9
+                c1.record(); c1.synchronize()
+                tot += c0.elapsed_time(c1)
+            line["cusparse_context_gflops"] = flops / (tot / 10 * 1e-3) / 1e9
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(rp_host.astype(np.uint32), c32.cpu().numpy().view(np.uint32),
                                                 v.cpu().numpy(), Bh.numpy(), k)

@@ -133,6 +133,41 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special(PanelArgs a, 
   if (col_ok) reinterpret_cast<float4*>(partial)[(size_t)item * k4 + c4] = acc;
 }
 
+// Few chunks (small matrices with a handful of long rows): one CTA per chunk, its workers take equal
+// slices of the 512 nz and are summed in worker order through shared memory, so that a short list of
+// chunks still fills the machine (one warp streaming 512 nz alone is pure DRAM latency).
+template <int KC>
+__global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special_cta(PanelArgs a, const int* __restrict__ special,
+                                                                      const int* __restrict__ special2,
+                                                                      float* __restrict__ partial) {
+  constexpr int LPR = KC / 4, RPW = 32 / LPR, NWK = PANEL_WARPS * RPW, SLICE = STHRESHOLD / NWK;
+  __shared__ __align__(16) float red[NWK][KC];
+  auto tile = cg::tiled_partition<LPR>(cg::this_thread_block());
+  const int sl = tile.thread_rank();
+  const int wk = (threadIdx.x >> 5) * RPW + (threadIdx.x & 31) / LPR;
+  const int item = blockIdx.x, kc0 = blockIdx.y * KC;
+  const unsigned k4 = a.k / 4;
+  const bool col_ok = kc0 / 4 + sl < (int)k4;
+  const int c4 = col_ok ? kc0 / 4 + sl : 0;
+  const int row = special[item], off = special2[item];
+  const int p = row / BH, r = row % BH;
+  const int cnt0 = a.mcsr_cnt[p], delta = a.mcsr_cnt[p + 1] - cnt0;
+  const int nch = a.spec_off[row + 1] - a.spec_off[row];
+  const int lo = a.mcsr_e[cnt0 * BH + (r + 1) * delta] - nch * STHRESHOLD + off + wk * SLICE;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  accum_global<LPR>(tile, lo, lo + SLICE, a.csr_e, a.csr_ev, reinterpret_cast<const float4*>(a.B) + c4, k4, acc);
+  reinterpret_cast<float4*>(red[wk])[sl] = acc;
+  __syncthreads();
+  if (wk == 0 && col_ok) {
+    float4 t = reinterpret_cast<const float4*>(red[0])[sl];
+    for (int w2 = 1; w2 < NWK; ++w2) {
+      const float4 x = reinterpret_cast<const float4*>(red[w2])[sl];
+      t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w;
+    }
+    reinterpret_cast<float4*>(partial)[(size_t)item * k4 + c4] = t;
+  }
+}
+
 // ---- panel kernel: one CTA per 128-row panel, nz-balanced inside the CTA ----------------------
 // The panel's handled nz (every row's [dense groups | sparse tail], i.e. everything except the
 // 512-chunks k_spmm_special takes from the END of long sparse groups) form one logical stream of
@@ -510,8 +545,13 @@ static int launch_aspt(const fx_tiles* t, const PanelArgs& a, int special_p, cud
   const int kchunks = ceil_div(a.k, KC);
   if (special_p > 0) {
     constexpr int RPW = 32 / (KC / 4);
-    dim3 g(ceil_div(special_p, PANEL_WARPS * RPW), kchunks);
-    k_spmm_special<KC><<<g, PANEL_WARPS * 32, 0, s>>>(a, d.special, d.special2, special_p, d.partial);
+    if (special_p < 148 * 8) {  // too few chunks to fill the SMs one warp each
+      dim3 g(special_p, kchunks);
+      k_spmm_special_cta<KC><<<g, PANEL_WARPS * 32, 0, s>>>(a, d.special, d.special2, d.partial);
+    } else {
+      dim3 g(ceil_div(special_p, PANEL_WARPS * RPW), kchunks);
+      k_spmm_special<KC><<<g, PANEL_WARPS * 32, 0, s>>>(a, d.special, d.special2, special_p, d.partial);
+    }
     FX_LAUNCH_CHECK();
   }
   static int minb = getenv("FLEX_MINB") ? atoi(getenv("FLEX_MINB")) : 3;
