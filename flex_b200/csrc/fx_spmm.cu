@@ -106,6 +106,7 @@ struct PanelArgs {
   const float* B;
   float* C;
   int npanel, nloc, k, BW, TS;
+  int split;  // CTAs per panel (>1 when the shard has too few panels to fill the GPU); cut at row boundaries
 };
 
 // ---- long-row chunks: partial[i,:] = sum over the i-th 512-nz chunk --------------------------
@@ -195,7 +196,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_panel(PanelArgs a, co
   const int sl = tile.thread_rank();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / LPR;
   const int w = warp * RPW + sub;
-  const int p = plist ? plist[blockIdx.x] : blockIdx.x, kc0 = blockIdx.y * KC;
+  const int pslot = blockIdx.x / a.split, part_q = blockIdx.x % a.split;
+  const int p = plist ? plist[pslot] : pslot, kc0 = blockIdx.y * KC;
   const int cnt0 = a.mcsr_cnt[p], delta = a.mcsr_cnt[p + 1] - cnt0;
   const int ntres = TILES ? min(delta - 1, a.TS) : 0;  // tiles resident in shared memory
   const unsigned k4 = a.k / 4;
@@ -248,7 +250,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_panel(PanelArgs a, co
     P[4 * lane + 1] = ex + v0; P[4 * lane + 2] = ex + v0 + v1; P[4 * lane + 3] = ex + v0 + v1 + v2; P[4 * lane + 4] = ex + s;
   }
   __syncthreads();
-  const int T = P[BH];
+  // this CTA's share of the panel: rows [rlo, rhi), cut where the stream crosses q/split of its length
+  int rlo = 0, rhi = BH;
+  if (a.split > 1) {
+    const int Tall = P[BH];
+    const int tlo = (int)((long long)Tall * part_q / a.split), thi = (int)((long long)Tall * (part_q + 1) / a.split);
+    int lo = 0, hi = BH;  // first r with P[r] >= tlo
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid] < tlo) lo = mid + 1; else hi = mid; }
+    rlo = part_q == 0 ? 0 : lo;
+    lo = 0; hi = BH;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid] < thi) lo = mid + 1; else hi = mid; }
+    rhi = part_q == a.split - 1 ? BH : lo;
+  }
+  const int T0 = P[rlo], T = P[rhi] - T0;
 
   auto finalize = [&](int r, float4 acc) {  // add the row's 512-chunk partials (chunk order) and store
     const int row = p * BH + r;
@@ -266,10 +280,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_panel(PanelArgs a, co
   // rows without any handled nz (empty, or consumed entirely by 512-chunks)
   for (int idx = threadIdx.x; idx < BH * LPR; idx += blockDim.x) {
     const int r = idx / LPR;  // idx % LPR == sl because blockDim is a multiple of LPR
-    if (P[r + 1] == P[r]) finalize(r, make_float4(0.f, 0.f, 0.f, 0.f));
+    if (r >= rlo && r < rhi && P[r + 1] == P[r]) finalize(r, make_float4(0.f, 0.f, 0.f, 0.f));
   }
 
-  const int a_pos = (int)((long long)T * w / NW), b_pos = (int)((long long)T * (w + 1) / NW);
+  const int a_pos = T0 + (int)((long long)T * w / NW), b_pos = T0 + (int)((long long)T * (w + 1) / NW);
   if (TILES && ntres > 0) mbar_wait(&bar, 0);
 
   if (a_pos < b_pos) {
@@ -507,7 +521,7 @@ static int launch_panels(const fx_aspt_dev& d, const PanelArgs& a, int kchunks, 
     constexpr int NW0 = WARPS * (32 / (KC / 4));
     const size_t ws = (size_t)2 * NW0 * KC * sizeof(float) + (size_t)NW0 * 2 * (KC / 4) * sizeof(uint2);
     FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
-    dim3 grid(d.npanel, kchunks);
+    dim3 grid(d.npanel * a.split, kchunks);
     k_spmm_panel<KC, WARPS, false, MINB><<<grid, WARPS * 32, ws, s>>>(a, nullptr);
     FX_LAUNCH_CHECK();
     return FX_OK;
@@ -521,7 +535,7 @@ static int launch_panels(const fx_aspt_dev& d, const PanelArgs& a, int kchunks, 
       FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)work_smem));
       carve = true;
     }
-    dim3 grid(d.n_plain, kchunks);
+    dim3 grid(d.n_plain * a.split, kchunks);
     k_spmm_panel<KC, WARPS, false, MINB><<<grid, WARPS * 32, work_smem, s>>>(a, d.n_tiled ? d.plist_plain : nullptr);
     FX_LAUNCH_CHECK();
   }
@@ -532,7 +546,7 @@ static int launch_panels(const fx_aspt_dev& d, const PanelArgs& a, int kchunks, 
       FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set = smem;
     }
-    dim3 grid(d.n_tiled, kchunks);
+    dim3 grid(d.n_tiled * a.split, kchunks);
     k_spmm_panel<KC, WARPS, true, MINB><<<grid, WARPS * 32, smem, s>>>(a, d.plist_tiled);
     FX_LAUNCH_CHECK();
   }
@@ -545,7 +559,8 @@ static int launch_aspt(const fx_tiles* t, const PanelArgs& a, int special_p, cud
   const int kchunks = ceil_div(a.k, KC);
   if (special_p > 0) {
     constexpr int RPW = 32 / (KC / 4);
-    if (special_p < 148 * 8) {  // too few chunks to fill the SMs one warp each
+    static const int cta_thr = getenv("FLEX_SPECIAL_CTA") ? atoi(getenv("FLEX_SPECIAL_CTA")) : 0x7fffffff;
+    if (special_p < cta_thr) {  // default: always (0.734 vs 0.758 ms on Reddit-shape, 0.126 vs 0.184 ms on a 1/8 shard)
       dim3 g(special_p, kchunks);
       k_spmm_special_cta<KC><<<g, PANEL_WARPS * 32, 0, s>>>(a, d.special, d.special2, d.partial);
     } else {
@@ -575,6 +590,15 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   a.partial = d.partial;
   a.B = B; a.C = C;
   a.npanel = d.npanel; a.nloc = t->row_end - t->row_begin; a.k = k; a.BW = d.BW;
+  {  // few panels (small matrix, or a small shard of a strong-scaling run): several CTAs per panel
+    static int sm = 0;
+    if (!sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev); }
+    const char* e = getenv("FLEX_SPLIT");
+    const int want = 6 * sm;  // ~2 waves at 3 CTAs per SM
+    const int kch = ceil_div(k, KC);
+    int sp = e ? atoi(e) : (d.npanel * kch >= want ? 1 : ceil_div(want, d.npanel * kch));
+    a.split = sp < 1 ? 1 : (sp > 8 ? 8 : sp);
+  }
   const size_t tile_bytes = (size_t)d.BW * KC * sizeof(float);
   int ts = d.max_tp;
   if (ts > MAX_TS) ts = MAX_TS;

@@ -212,3 +212,22 @@ def test_permute_rows(orc):
     d2.unpermute_rows(Cd.data_ptr(), Od.data_ptr(), k)
     torch.cuda.synchronize()
     assert_close(orc, orc.spmm_ref(rp, c, v, B), Od.cpu().numpy(), rp)
+
+
+@pytest.mark.parametrize("split", ["1", "2", "5", "8"])
+@pytest.mark.parametrize("k", [32, 128])
+def test_panel_split(orc, monkeypatch, split, k):
+    """Several CTAs per panel (small shards of a strong-scaling run): cut at row boundaries, every C
+    element still written once."""
+    monkeypatch.setenv("FLEX_SPLIT", split)
+    n = 128 * 5 + 77
+    rp, c, v = random_csr(n, 12, 31, hubs=3, blocks=6)
+    rp = rp.copy()
+    dl = fx.DataLoader.from_arrays(rp, c, v, k)
+    B = rand_dense(n, k, 5)
+    gold = orc.spmm_ref(rp, c, v, B)
+    for tiles in ("0", "1"):
+        monkeypatch.setenv("FLEX_TILES", tiles)
+        mat = fx.Mat(dl, fmt="aspt", bw=128)
+        assert_close(orc, gold, run_spmm(mat, B, n), rp)
+        mat.free()
