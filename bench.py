@@ -46,6 +46,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(workload, k):
+    """DRAM bytes per step from the committed ncu capture of this workload (profiles/r1_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(p)).get(f"{workload}:{k}", {}).get("bytes")
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(n, nnz, k):
     """CSR A (rowptr + col,val) + B read once + C written once."""
     return 4 * (n + 1) + 8 * nnz + 4 * n * k + 4 * n * k
@@ -334,9 +343,12 @@ def main():
             "config": workload_config(args, k, n, nnz),
             "tPre_ms": min(tpre), "tPre_over_tElap": min(tpre) / ms_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": None, "peak_source": peak_src,
+                         "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "traffic": measured_traffic(args.workload, k) if (world == 1 and args.order == "ovo" and not args.shuffle and args.fmt == "aspt") else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes,
-                         "kernel": "k_spmm_panel (+ k_spmm_special for 512-nz chunks of long rows); timed together"},
+                         "kernel": "k_spmm_panel (76 % of the step) + k_spmm_special_cta (512-nz chunks of long rows); one step = both, timed together; "
+                                   "the bound that binds is the L2->SM gather path (nnz*k*4 bytes), see DESIGN.md section 5"},
             "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(4 * n * k), "d2h_bytes_per_step": int(4 * (hi - lo) * k)},
             "gpu_launches": int(launches),

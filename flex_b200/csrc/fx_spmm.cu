@@ -504,7 +504,7 @@ static int panel_warps() {
   if (!w) {
     const char* e = getenv("FLEX_PANEL_WARPS");
     w = e ? atoi(e) : 16;
-    if (w != 8 && w != 16 && w != 32) w = 16;
+    if (w != 8 && w != 16 && w != 24 && w != 32) w = 16;
   }
   return w;
 }
@@ -573,6 +573,7 @@ static int launch_aspt(const fx_tiles* t, const PanelArgs& a, int special_p, cud
   switch (panel_warps()) {
     case 8: return minb >= 6 ? launch_panels<KC, 8, 6>(d, a, kchunks, s) : launch_panels<KC, 8, 1>(d, a, kchunks, s);
     case 32: return launch_panels<KC, 32, 1>(d, a, kchunks, s);
+    case 24: return launch_panels<KC, 24, 2>(d, a, kchunks, s);
     default: return minb >= 3 ? launch_panels<KC, 16, 3>(d, a, kchunks, s) : launch_panels<KC, 16, 1>(d, a, kchunks, s);
   }
 }
