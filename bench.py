@@ -30,7 +30,7 @@ def parse():
     ap.add_argument("--workload", default=os.environ.get("FLEX_WORKLOAD", "reddit"))
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--fmt", default="aspt")
-    ap.add_argument("--order", default="ovo", choices=["ovo", "deg", "rcm", "gor"])
+    ap.add_argument("--order", default="ovo", choices=["ovo", "deg", "rcm", "gor", "dfs", "rbt"])
     ap.add_argument("--shuffle", action="store_true", help="hide the planted block order of the synthetic graph")
     ap.add_argument("--impl", default="flex_b200", choices=["flex_b200", "reference"])
     ap.add_argument("--allgather", action="store_true", help="also time the optional NCCL all-gather of C")
@@ -235,7 +235,7 @@ def main():
     if need_host:
         dl0 = fx.DataLoader.from_arrays(rp_host.astype(np.uint32), c.cpu().numpy().astype(np.uint32), v.cpu().numpy(), k,
                                         args.workload + ".csv")
-        dl = dl0.reorder({"deg": fx.FX_ORDER_DEG, "rcm": fx.FX_ORDER_RCM, "gor": fx.FX_ORDER_GOR}[args.order])
+        dl = dl0.reorder({"deg": fx.FX_ORDER_DEG, "rcm": fx.FX_ORDER_RCM, "gor": fx.FX_ORDER_GOR, "dfs": fx.FX_ORDER_DFS, "rbt": fx.FX_ORDER_RBT}[args.order])
         rp_host = dl.rowPtr.astype(np.int64)
     else:
         dl = fx.DataLoader.from_device(n, nnz, rp32.data_ptr(), c32.data_ptr(), v.data_ptr(), k, args.workload + ".csv")

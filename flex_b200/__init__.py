@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBPATH = os.path.join(_HERE, "libflexb200.so")
 _lib = None
 
-FX_ORDER_OVO, FX_ORDER_DEG, FX_ORDER_RCM, FX_ORDER_GOR = 0, 1, 2, 3
+FX_ORDER_OVO, FX_ORDER_DEG, FX_ORDER_RCM, FX_ORDER_GOR, FX_ORDER_DFS, FX_ORDER_RBT = 0, 1, 2, 3, 4, 5
 FX_FMT_CSR, FX_FMT_ASPT, FX_FMT_TILE, FX_FMT_SEG, FX_FMT_PILLAR = 0, 1, 2, 3, 4
 _FMT = {"csr": FX_FMT_CSR, "aspt": FX_FMT_ASPT, "tile": FX_FMT_TILE, "seg": FX_FMT_SEG,
         "pillar": FX_FMT_PILLAR}
@@ -272,6 +272,14 @@ def DataLoaderRcm(dl):
 
 def DataLoaderGorder(dl):
     return dl.reorder(FX_ORDER_GOR)
+
+
+def DataLoaderDFS(dl):
+    return dl.reorder(FX_ORDER_DFS)
+
+
+def DataLoaderRabbit(dl):
+    return dl.reorder(FX_ORDER_RBT)
 
 
 class Mat:

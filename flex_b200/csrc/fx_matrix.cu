@@ -141,9 +141,9 @@ void fill_info(fx_matrix* m, const std::string& file_name, int order) {
   m->info.c = class_count(file_name);
   std::string g = file_name.substr(0, file_name.find("."));  // DataLoader.cu:12
   snprintf(m->info.graph_name, sizeof(m->info.graph_name), "%s", g.c_str());
-  static const char* abbr[] = {"OVO", "DEG", "RCM", "GOR"};
+  static const char* abbr[] = {"OVO", "DEG", "RCM", "GOR", "DFS", "RBT", "OVO", "OVO"};
   m->info.order = order;
-  snprintf(m->info.order_abbr, sizeof(m->info.order_abbr), "%s", abbr[order & 3]);
+  snprintf(m->info.order_abbr, sizeof(m->info.order_abbr), "%s", abbr[order & 7]);
   int64_t uni = 0;  // DataLoader.cu:24-27
   for (int64_t i = 1; i <= m->n; ++i) uni += (m->rowptr[i] - m->rowptr[i - 1] == 1);
   m->info.uni_nb = uni;
@@ -162,6 +162,10 @@ int finish_matrix(fx_matrix* m, const std::string& name, int order, bool do_uplo
   return FX_OK;
 }
 int ensure_device(const fx_matrix* m) { return upload(const_cast<fx_matrix*>(m)); }
+int ensure_census(const fx_matrix* m) {
+  if (!m->census_done && !m->col.empty()) census(const_cast<fx_matrix*>(m));
+  return FX_OK;
+}
 }  // namespace fx
 
 extern "C" int fx_csr_load(const char* path, int k, fx_matrix** out) {

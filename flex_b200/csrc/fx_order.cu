@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <map>
 #include <numeric>
 
 #include "fx_common.cuh"
@@ -279,6 +280,121 @@ int order_gorder(const fx_matrix* m, int window, std::vector<ul>& rank) {
   for (int64_t p = 0; p < n; ++p) rg[order[p]] = (ul)p;
   rank.assign(n, 0);
   for (int64_t u = 0; u < n; ++u) rank[u] = rg[rrcm[u]];  // order_gorder.cu:26-29
+  return FX_OK;
+}
+
+// ---- DFS order (DataLoaderDFS, DataLoader.cu:324-385) ---------------------------------------
+// Pre-order numbering of an iterative depth-first search from vertex 0, neighbours in column order,
+// restarted at the next unvisited vertex.  rank[old] = new.
+int order_dfs(const fx_matrix* m, std::vector<ul>& rank) {
+  const int64_t n = m->n;
+  rank.assign(n, 0);
+  std::vector<uint8_t> seen(n, 0);
+  std::vector<std::pair<uint32_t, uint32_t>> stack;  // (cursor, end) into col
+  ul next = 0;
+  for (int64_t root = 0; root < n; ++root) {
+    if (seen[root]) continue;
+    seen[root] = 1;
+    rank[root] = next++;
+    stack.push_back({m->rowptr[root], m->rowptr[root + 1]});
+    while (!stack.empty()) {
+      auto& it = stack.back();
+      while (it.first < it.second && seen[m->col[it.first]]) ++it.first;
+      if (it.first >= it.second) { stack.pop_back(); continue; }
+      const uint32_t v = m->col[it.first++];
+      seen[v] = 1;
+      rank[v] = next++;
+      stack.push_back({m->rowptr[v], m->rowptr[v + 1]});
+    }
+  }
+  return FX_OK;
+}
+
+// ---- Rabbit order (DataLoaderRabbit, DataLoader.cu:455-655; Shiokawa'13 iterative variant) ----
+// Incremental modularity merging (opt_iterative, no hub grouping, cluster shyness 1), dendrogram
+// leaves in order.  vo_mp[new] = old is produced directly.  The per-round vertex order comes from
+// an UNSTABLE sort by current degree in the reference (ranges::sort); the same libstdc++ std::sort
+// is used here on the same sequence so that ties fall the same way.
+int order_rabbit(const fx_matrix* m, bool is_directed, std::vector<int32_t>& vo_mp) {
+  const int64_t n = m->n;
+  struct Vtx {
+    std::map<int, int> w;       // modularity weights to neighbouring clusters
+    int left = -1, right = -1;  // dendrogram: cluster node = (left subtree root, right subtree root)
+    int tree = -1;              // current root node id of this vertex's tree, -1 once merged away
+    int deg = 0, round = 0;
+  };
+  std::vector<Vtx> g(n);
+  // dendrogram nodes: ids [0,n) are leaves, id n+u is the cluster node created when u was merged
+  std::vector<int> lch(2 * n, -1), rch(2 * n, -1);
+  long long n_edges = 0;
+  std::vector<uint32_t> cur(n), nxt;
+  for (int64_t v = 0; v < n; ++v) {
+    for (uint32_t e = m->rowptr[v]; e < m->rowptr[v + 1]; ++e) {
+      const int d = (int)m->col[e];
+      if (d != v) {
+        g[v].w[d] = 1;
+        if (is_directed) g[d].w[(int)v] = 1;  // force_undirected = dl.is_directed
+      }
+    }
+    // as in the reference (DataLoader.cu:527), the degree is taken HERE: it counts the reverse edges
+    // that lower-numbered vertices have already inserted, not those higher-numbered ones add later
+    g[v].deg = (int)g[v].w.size();
+    n_edges += g[v].deg;
+    g[v].tree = (int)v;
+    cur[v] = (uint32_t)v;
+  }
+  const double two_m_inv = 1.0 / double(2 * n_edges);
+  for (int round = 1; !cur.empty(); ++round) {
+    std::sort(cur.begin(), cur.end(), [&](uint32_t a, uint32_t b) { return g[a].deg < g[b].deg; });
+    for (uint32_t u : cur) {
+      Vtx& uo = g[u];
+      if (uo.round == round) continue;
+      double dq_max = -1;
+      int v = -1;
+      const double dv_2m = uo.deg * two_m_inv;
+      for (auto& [d, w] : uo.w) {
+        const double dq = w - g[d].deg * dv_2m;
+        if (dq > dq_max) { dq_max = dq; v = d; }
+      }
+      if (dq_max <= 0) continue;
+      Vtx& vo = g[v];
+      vo.deg += uo.deg;
+      for (auto& [d, w] : uo.w) {
+        if (d == v) continue;
+        vo.w[d] += w;
+        auto& dw = g[d].w;
+        auto it = dw.find((int)u);
+        if (it == dw.end()) continue;
+        dw[v] += it->second;
+        dw.erase((int)u);
+      }
+      vo.w.erase((int)u);
+      lch[n + u] = vo.tree;  // Tree_Node(vo.tree_node, uo.tree_node)
+      rch[n + u] = uo.tree;
+      uo.tree = -1;
+      vo.tree = (int)(n + u);
+      if (vo.round == round) continue;
+      vo.round = round;
+      nxt.push_back((uint32_t)v);
+    }
+    if (!(nxt.size() < cur.size())) { set_error("Rabbit: no progress (assert DataLoader.cu:585)"); return FX_ERR_FORMAT; }
+    std::swap(cur, nxt);
+    nxt.clear();
+  }
+  vo_mp.clear();
+  vo_mp.reserve(n);
+  std::vector<int> st;
+  for (int64_t v = 0; v < n; ++v) {
+    if (g[v].tree < 0) continue;
+    st.push_back(g[v].tree);
+    while (!st.empty()) {  // leaves left to right
+      const int node = st.back();
+      st.pop_back();
+      if (node < n) { vo_mp.push_back(node); continue; }
+      st.push_back(rch[node]);
+      st.push_back(lch[node]);
+    }
+  }
   return FX_OK;
 }
 

@@ -16,6 +16,9 @@ int finish_matrix(fx_matrix* m, const std::string& name, int order, bool do_uplo
 int order_deg(const fx_matrix* m, bool desc, std::vector<uint64_t>& rank);
 int order_rcm(const fx_matrix* m, std::vector<uint64_t>& rank);
 int order_gorder(const fx_matrix* m, int window, std::vector<uint64_t>& rank);
+int order_dfs(const fx_matrix* m, std::vector<uint64_t>& rank);
+int order_rabbit(const fx_matrix* m, bool is_directed, std::vector<int32_t>& vo_mp);
+int ensure_census(const fx_matrix* m);
 
 // rank[old] = new.  Produces vo_mp[new]=old and the permuted CSR with ascending columns.
 int perm_apply(const fx_matrix* src, const uint64_t* rank, fx_matrix* dst) {
@@ -86,6 +89,17 @@ extern "C" int fx_reorder(const fx_matrix* m, int order, fx_matrix** out) {
     case FX_ORDER_DEG: rc = fx::order_deg(m, true, rank); break;   // DataLoader.cu:672 order_deg(h,true)
     case FX_ORDER_RCM: rc = fx::order_rcm(m, rank); break;         // DataLoader.cu:737
     case FX_ORDER_GOR: rc = fx::order_gorder(m, 3, rank); break;   // DataLoader.cu:803 window=3
+    case FX_ORDER_DFS: rc = fx::order_dfs(m, rank); break;         // DataLoader.cu:324-385
+    case FX_ORDER_RBT: {                                           // DataLoader.cu:455-655
+      std::vector<int32_t> vo;
+      fx::ensure_census(m);
+      rc = fx::order_rabbit(m, m->info.is_directed != 0, vo);
+      if (rc == FX_OK) {
+        rank.resize(m->n);
+        for (int64_t i = 0; i < m->n; ++i) rank[vo[i]] = (uint64_t)i;
+      }
+      break;
+    }
     default: fx::set_error("unknown order %d", order); return FX_ERR_ARG;
   }
   if (rc != FX_OK) return rc;

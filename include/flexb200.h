@@ -33,7 +33,9 @@ typedef enum { /* DataLoader::vertex_order_abbr, DataLoader.cu:14,326,457,660,72
   FX_ORDER_OVO = 0, /* original vertex order */
   FX_ORDER_DEG = 1, /* DataLoaderDeg    DataLoader.cu:658-721 */
   FX_ORDER_RCM = 2, /* DataLoaderRcm    DataLoader.cu:723-787 */
-  FX_ORDER_GOR = 3  /* DataLoaderGorder DataLoader.cu:789-857 */
+  FX_ORDER_GOR = 3, /* DataLoaderGorder DataLoader.cu:789-857 */
+  FX_ORDER_DFS = 4, /* DataLoaderDFS    DataLoader.cu:324-453 */
+  FX_ORDER_RBT = 5  /* DataLoaderRabbit DataLoader.cu:455-655 */
 } fx_order;
 
 typedef enum {
@@ -53,7 +55,7 @@ typedef struct { /* DataLoader public fields, DataLoader.cuh:57-71 */
   int64_t n_edges_one_way, n_edges_asymmetric;
   int32_t order;          /* fx_order */
   char graph_name[64];    /* basename without extension, DataLoader.cu:11-12 */
-  char order_abbr[4];     /* "OVO","DEG","RCM","GOR" */
+  char order_abbr[4];     /* "OVO","DEG","RCM","GOR","DFS","RBT" */
 } fx_matrix_info;
 
 typedef struct {

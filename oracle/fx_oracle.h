@@ -79,6 +79,9 @@ void orc_permute_rows(int64_t n, int k, const int32_t *vo_mp, const float *B, fl
 void orc_order_deg(int64_t n, const uint32_t *rowptr, const uint32_t *col, int desc, uint64_t *rank);
 void orc_order_rcm(int64_t n, const uint32_t *rowptr, const uint32_t *col, uint64_t *rank);
 int orc_order_gorder(int64_t n, const uint32_t *rowptr, const uint32_t *col, int window, uint64_t *rank);
+/* N1: DataLoaderDFS (DataLoader.cu:324-385) rank[old]=new; DataLoaderRabbit (:455-655) vo_mp[new]=old */
+void orc_order_dfs(int64_t n, const uint32_t *rowptr, const uint32_t *col, uint64_t *rank);
+int orc_order_rabbit(int64_t n, const uint32_t *rowptr, const uint32_t *col, int is_directed, int32_t *vo_mp);
 
 /* ---- A1: ASpT tile builder, canonical (aspt/sspmm_128.cu:831-1087,1207-1333) ---- */
 typedef struct {

@@ -113,6 +113,9 @@ def lib():
     L.orc_order_rcm.argtypes = [C.c_int64, u32p, u32p, u64p]
     L.orc_order_gorder.argtypes = [C.c_int64, u32p, u32p, C.c_int, u64p]
     L.orc_order_gorder.restype = C.c_int
+    L.orc_order_dfs.argtypes = [C.c_int64, u32p, u32p, u64p]
+    L.orc_order_rabbit.argtypes = [C.c_int64, u32p, u32p, C.c_int, i32p]
+    L.orc_order_rabbit.restype = C.c_int
     L.orc_flex_tile_build.argtypes = [C.c_int, u32p, u32p, f32p, C.c_int, C.c_int, C.c_int, C.POINTER(OrcFlexTile)]
     L.orc_flextile_free.argtypes = [C.POINTER(OrcFlexTile)]
     L.orc_flextile_spmm.argtypes = [C.POINTER(OrcFlexTile), f32p, C.c_int, f32p]
@@ -239,10 +242,25 @@ def order(kind, rowptr, col, window=3):
         lib().orc_order_deg(n, rowptr, col, 1, rank)
     elif kind == "rcm":
         lib().orc_order_rcm(n, rowptr, col, rank)
+    elif kind == "dfs":
+        lib().orc_order_dfs(n, rowptr, col, rank)
+    elif kind == "rbt":
+        raise ValueError("use order_rabbit (it yields vo_mp and needs is_directed)")
     else:
         if lib().orc_order_gorder(n, rowptr, col, window, rank) != 0:
             raise ValueError("gorder: isolated vertex")
     return rank
+
+
+def order_rabbit(rowptr, col, is_directed):
+    """vo_mp[new] = old of DataLoaderRabbit (DataLoader.cu:455-655)."""
+    rowptr = np.ascontiguousarray(rowptr, np.uint32)
+    col = np.ascontiguousarray(col, np.uint32)
+    n = len(rowptr) - 1
+    vo = np.empty(n, np.int32)
+    if lib().orc_order_rabbit(n, rowptr, col, int(bool(is_directed)), vo) != 0:
+        raise ValueError("rabbit: no progress")
+    return vo
 
 
 class Aspt:

@@ -8,7 +8,7 @@
 // A separate process per call: the reference asserts (abort) on inputs it does not support.
 //
 //   flexref load  <csv> <out>
-//   flexref order <csv> <out> deg|rcm|gor          (DataLoaderDeg/Rcm/Gorder DataLoader.cu:658-857)
+//   flexref order <csv> <out> deg|rcm|gor|dfs|rbt  (DataLoaderDeg/Rcm/Gorder/DFS/Rabbit DataLoader.cu:324-857)
 //   flexref rank  <csv> <out> deg|rcm|gor          (order_deg/order_rcm/complete_gorder)
 //   flexref seg   <csv> <out> <tm>                 (Mat::csr2seg_Cmajor per panel, mat.cu:1192)
 //   flexref diag  <csv> <out> <tm> <n_sm>          (Mat::csr2_DiagTiling mat.cu:680)
@@ -63,6 +63,8 @@ int main(int argc, char** argv) {
     std::string o = argv[4];
     if (o == "deg") { DataLoaderDeg r(dl); dump_loader(r); }
     else if (o == "rcm") { DataLoaderRcm r(dl); dump_loader(r); }
+    else if (o == "dfs") { DataLoaderDFS r(dl); dump_loader(r); }
+    else if (o == "rbt") { DataLoaderRabbit r(dl); dump_loader(r); }
     else { DataLoaderGorder r(dl); dump_loader(r); }
   } else if (cmd == "rank") {
     std::string o = argv[4];

@@ -35,6 +35,8 @@ def main():
         calls.append((name, path, "load", ()))
         for kind in ("deg", "rcm", "gor"):
             calls += [(name, path, "rank", (kind,)), (name, path, "order", (kind,))]
+        for kind in ("dfs", "rbt"):
+            calls.append((name, path, "order", (kind,)))
         for tm in (2, 4, 8, 16):
             calls.append((name, path, "seg", (tm,)))
         for tm, tn in ((2, 2), (4, 4), (8, 4), (16, 4), (4, 32)):

@@ -157,3 +157,26 @@ def test_diag_tiling_pinned(orc, tmp_path, n_sm):
             assert np.array_equal(r[f], d[f]), (name, n_sm, f)
         assert int(r["n_segs"]) == d["n_segs"]
         assert abs(r["empty_wp_p"] - d["empty_wp_p"]) < 1e-4 and abs(r["band_nz_p"] - d["band_nz_p"]) < 1e-4
+
+
+@pytest.mark.parametrize("kind", ["dfs", "rbt"])
+def test_next_orderings_pinned(orc, tmp_path, kind):
+    """N1: DataLoaderDFS / DataLoaderRabbit -- oracle and product against the reference."""
+    tag = {"dfs": fx.FX_ORDER_DFS, "rbt": fx.FX_ORDER_RBT}[kind]
+    for name, path in graphs(tmp_path):
+        r = reference("order", name, path, kind)
+        if r is None:
+            continue
+        m = orc.csv_load(path)
+        if kind == "dfs":
+            rank = orc.order("dfs", m["rowptr"], m["col"])
+            vo = np.empty(m["n"], np.int32)
+            vo[rank.astype(np.int64)] = np.arange(m["n"], dtype=np.int32)
+        else:
+            vo = orc.order_rabbit(m["rowptr"], m["col"], m["is_directed"])
+        assert np.array_equal(vo, r["vo_mp"]), (name, kind, "oracle")
+        d2 = fx.DataLoader(path, 4).reorder(tag)
+        a, b, c = d2.host_csr()
+        assert np.array_equal(d2.vo_mp, r["vo_mp"]), (name, kind, "product")
+        assert np.array_equal(a, r["rowPtr"]) and np.array_equal(b, r["col"]) and np.array_equal(c, r["vals"])
+        assert d2.vertex_order_abbr == kind.upper()
