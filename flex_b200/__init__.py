@@ -99,7 +99,7 @@ class Report(C.Structure):
 # every extern "C" symbol include/flexb200.h declares (tests check the library exports all)
 ABI_SYMBOLS = [
     "fx_last_error", "fx_version", "fx_launch_count", "fx_device_sm_count", "fx_csr_load",
-    "fx_csr_from_arrays", "fx_csr_from_device", "fx_matrix_get_info", "fx_matrix_host_csr",
+    "fx_csr_from_arrays", "fx_csr_from_device", "fx_mtx_load", "fx_csr_write_csv", "fx_csr_save_bin", "fx_csr_load_bin", "fx_matrix_get_info", "fx_matrix_host_csr",
     "fx_matrix_device_csr", "fx_matrix_free", "fx_rand_B", "fx_reorder", "fx_reorder_with_rank",
     "fx_permutation", "fx_permute_rows", "fx_unpermute_rows", "fx_build", "fx_rebuild",
     "fx_tiles_export_aspt", "fx_tiles_export_tile", "fx_tiles_export_seg", "fx_tiles_export_pillar", "fx_tiles_free", "fx_spmm", "fx_spmm_host", "fx_check",
@@ -122,6 +122,10 @@ def lib():
     L.fx_csr_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.fx_csr_from_arrays.argtypes = [C.c_int64, C.c_int64, vp, vp, vp, C.c_int, C.c_char_p, C.POINTER(vp)]
     L.fx_csr_from_device.argtypes = [C.c_int64, C.c_int64, vp, vp, vp, C.c_int, C.c_char_p, C.POINTER(vp)]
+    L.fx_mtx_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.fx_csr_write_csv.argtypes = [vp, C.c_char_p]
+    L.fx_csr_save_bin.argtypes = [vp, C.c_char_p]
+    L.fx_csr_load_bin.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.fx_matrix_get_info.argtypes = [vp, C.POINTER(MatrixInfo)]
     L.fx_matrix_host_csr.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.fx_matrix_device_csr.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
@@ -186,6 +190,25 @@ class DataLoader:
         _ck(lib().fx_csr_from_arrays(len(rowptr) - 1, len(col), rowptr.ctypes.data, col.ctypes.data,
                                      val.ctypes.data, int(k), name.encode(), C.byref(h)))
         return cls(_handle=h)
+
+    @classmethod
+    def from_mtx(cls, path, k):
+        """Matrix Market file, converted as data/SuiteSparse/mtx2csr.cc + DataLoader would."""
+        h = C.c_void_p()
+        _ck(lib().fx_mtx_load(os.fsencode(path), int(k), C.byref(h)))
+        return cls(_handle=h)
+
+    @classmethod
+    def from_bin(cls, path, k=0):
+        h = C.c_void_p()
+        _ck(lib().fx_csr_load_bin(os.fsencode(path), int(k), C.byref(h)))
+        return cls(_handle=h)
+
+    def save_bin(self, path):
+        _ck(lib().fx_csr_save_bin(self._h, os.fsencode(path)))
+
+    def write_csv(self, path):
+        _ck(lib().fx_csr_write_csv(self._h, os.fsencode(path)))
 
     @classmethod
     def from_device(cls, n, nnz, rowptr_ptr, col_ptr, val_ptr, k, name="device.csv"):

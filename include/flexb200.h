@@ -132,6 +132,15 @@ int fx_csr_from_arrays(int64_t n, int64_t nnz, const uint32_t *rowptr, const uin
 /* CSR already resident in HBM (arrays are copied device-to-device) */
 int fx_csr_from_device(int64_t n, int64_t nnz, const uint32_t *rowptr_dev, const uint32_t *col_dev,
                        const float *val_dev, int k, const char *name, fx_matrix **out);
+/* N2: Matrix Market coordinate file -> CSR, as data/SuiteSparse/mtx2csr.cc (mmio_allinone :57-222 +
+ * the 6-significant-digit text round trip of writeCSR2csv :224-246) followed by DataLoader would
+ * load it; rows sorted by column */
+int fx_mtx_load(const char *path, int k, fx_matrix **out);
+/* the 3-line CSV writer of mtx2csr.cc:224-246 */
+int fx_csr_write_csv(const fx_matrix *m, const char *path);
+/* binary CSR cache (no reference counterpart: replaces re-parsing gigabytes of ASCII) */
+int fx_csr_save_bin(const fx_matrix *m, const char *path);
+int fx_csr_load_bin(const char *path, int k /* 0 = stored k */, fx_matrix **out);
 int fx_matrix_get_info(const fx_matrix *m, fx_matrix_info *info);
 /* host views of rowPtr/col/vals (DataLoader.cuh:32-34); NULL if created from device arrays */
 int fx_matrix_host_csr(const fx_matrix *m, const uint32_t **rowptr, const uint32_t **col,

@@ -19,6 +19,10 @@ for f in mat DataLoader order_deg order_rcm order_gorder edgelist adjlist algo_b
 done
 wait
 $CXX -std=c++20 -O2 -w -I"$HERE/ref_stubs" -I"$REF" "$HERE/ref_driver.cc" "$OUT"/obj/*.o -o "$OUT/flexref"
+# the reference's Matrix Market -> CSV converter (data/SuiteSparse/mtx2csr.cc), unmodified
+if [ ! -f "$OUT/mtx2csr" ]; then
+  $CXX -O2 -w -I"$REF/data/SuiteSparse" "$REF/data/SuiteSparse/mtx2csr.cc" -o "$OUT/mtx2csr" || echo "mtx2csr did not build"
+fi
 NVCC=/usr/local/cuda/bin/nvcc
 if [ -x "$NVCC" ] && [ "${REF_ASPT:-1}" = "1" ]; then
   for b in sspmm_128 sspmm_32; do
