@@ -30,6 +30,9 @@ def parse():
     ap.add_argument("--workload", default=os.environ.get("FLEX_WORKLOAD", "reddit"))
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--fmt", default="aspt")
+    ap.add_argument("--tc-threshold", type=int, default=0)
+    ap.add_argument("--tc-width", type=int, default=0)
+    ap.add_argument("--tc-min-gain", type=int, default=0)
     ap.add_argument("--order", default="ovo", choices=["ovo", "deg", "rcm", "gor", "dfs", "rbt"])
     ap.add_argument("--shuffle", action="store_true", help="hide the planted block order of the synthetic graph")
     ap.add_argument("--impl", default="flex_b200", choices=["flex_b200", "reference"])
@@ -242,7 +245,8 @@ def main():
     from flex_b200.shard import panel_shards
     shards = panel_shards(rp_host, world)
     lo, hi = shards[rank]
-    mat = fx.Mat(dl, fmt=args.fmt, row_begin=lo, row_end=hi)
+    mat = fx.Mat(dl, fmt=args.fmt, row_begin=lo, row_end=hi, tc_threshold=args.tc_threshold, tc_width=args.tc_width,
+                 tc_min_gain=args.tc_min_gain)
     tpre = [mat.tPre_ms] + [mat.rebuild() for _ in range(3)]
     B = synth.dense_B(n, k, device=dev)
     Cd = torch.empty((hi - lo, k), dtype=torch.float32, device=dev)

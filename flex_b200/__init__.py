@@ -23,9 +23,9 @@ _LIBPATH = os.path.join(_HERE, "libflexb200.so")
 _lib = None
 
 FX_ORDER_OVO, FX_ORDER_DEG, FX_ORDER_RCM, FX_ORDER_GOR, FX_ORDER_DFS, FX_ORDER_RBT = 0, 1, 2, 3, 4, 5
-FX_FMT_CSR, FX_FMT_ASPT, FX_FMT_TILE, FX_FMT_SEG, FX_FMT_PILLAR = 0, 1, 2, 3, 4
+FX_FMT_CSR, FX_FMT_ASPT, FX_FMT_TILE, FX_FMT_SEG, FX_FMT_PILLAR, FX_FMT_TCW = 0, 1, 2, 3, 4, 5
 _FMT = {"csr": FX_FMT_CSR, "aspt": FX_FMT_ASPT, "tile": FX_FMT_TILE, "seg": FX_FMT_SEG,
-        "pillar": FX_FMT_PILLAR}
+        "pillar": FX_FMT_PILLAR, "tcw": FX_FMT_TCW}
 
 
 class FlexError(RuntimeError):
@@ -44,7 +44,8 @@ class MatrixInfo(C.Structure):
 class BuildOpts(C.Structure):
     _fields_ = [("format", C.c_int32), ("tm", C.c_int32), ("tn", C.c_int32), ("bw", C.c_int32),
                 ("nnz_limit", C.c_int32), ("n_sm", C.c_int32), ("row_begin", C.c_int32),
-                ("row_end", C.c_int32), ("cmajor", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("row_end", C.c_int32), ("cmajor", C.c_int32), ("tc_threshold", C.c_int32),
+                ("tc_width", C.c_int32), ("tc_min_gain", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class AsptArrays(C.Structure):
@@ -90,6 +91,16 @@ class PillarArrays(C.Structure):
                 ("empty_wp_p", C.c_float), ("band_nz_p", C.c_float)]
 
 
+class TcwArrays(C.Structure):
+    _fields_ = [("n", C.c_int32), ("nr", C.c_int32), ("npanel", C.c_int32), ("W", C.c_int32), ("T", C.c_int32),
+                ("min_gain", C.c_int32), ("ntc", C.c_int32), ("dropped", C.c_int32),
+                ("win_nnz", C.c_int64), ("rest_nnz", C.c_int64),
+                ("tc_cols", C.POINTER(C.c_int32)), ("tc_ncol", C.POINTER(C.c_int32)),
+                ("win_cptr", C.POINTER(C.c_int32)), ("win_code", C.POINTER(C.c_uint16)),
+                ("win_val", C.POINTER(C.c_float)), ("rest_rowptr", C.POINTER(C.c_uint32)),
+                ("rest_col", C.POINTER(C.c_uint32)), ("rest_val", C.POINTER(C.c_float))]
+
+
 class Report(C.Structure):
     _fields_ = [("tPre_ms", C.c_float), ("tElap_ms", C.c_float), ("gflops", C.c_double),
                 ("tpre_over_telap", C.c_double), ("errs_flex", C.c_int64),
@@ -102,7 +113,7 @@ ABI_SYMBOLS = [
     "fx_csr_from_arrays", "fx_csr_from_device", "fx_mtx_load", "fx_csr_write_csv", "fx_csr_save_bin", "fx_csr_load_bin", "fx_matrix_get_info", "fx_matrix_host_csr",
     "fx_matrix_device_csr", "fx_matrix_free", "fx_rand_B", "fx_reorder", "fx_reorder_with_rank",
     "fx_permutation", "fx_permute_rows", "fx_unpermute_rows", "fx_build", "fx_rebuild",
-    "fx_tiles_export_aspt", "fx_tiles_export_tile", "fx_tiles_export_seg", "fx_tiles_export_pillar", "fx_tiles_free", "fx_spmm", "fx_spmm_host", "fx_check",
+    "fx_tiles_export_aspt", "fx_tiles_export_tile", "fx_tiles_export_seg", "fx_tiles_export_pillar", "fx_tiles_export_tcw", "fx_tiles_free", "fx_spmm", "fx_spmm_host", "fx_check",
 ]
 
 
@@ -143,6 +154,7 @@ def lib():
     L.fx_tiles_export_tile.argtypes = [vp, C.POINTER(TileArrays)]
     L.fx_tiles_export_seg.argtypes = [vp, C.POINTER(SegArrays)]
     L.fx_tiles_export_pillar.argtypes = [vp, C.POINTER(PillarArrays)]
+    L.fx_tiles_export_tcw.argtypes = [vp, C.POINTER(TcwArrays)]
     L.fx_tiles_free.argtypes = [vp]
     L.fx_tiles_free.restype = None
     L.fx_spmm.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(C.c_float)]
@@ -309,13 +321,15 @@ class Mat:
     """Tile format built on the GPU (Mat::Mat + csr2tile/transfer/launch_prep, mat.cuh:74-182;
     ASpT: the pre-process section of process(), aspt/sspmm_128.cu:1207-1333)."""
 
-    def __init__(self, dl, fmt="aspt", tm=4, tn=4, bw=0, row_begin=0, row_end=0, n_sm=0, cmajor=0, nnz_limit=0):
+    def __init__(self, dl, fmt="aspt", tm=4, tn=4, bw=0, row_begin=0, row_end=0, n_sm=0, cmajor=0, nnz_limit=0,
+                 tc_threshold=0, tc_width=0, tc_min_gain=0):
         self.dl = dl
         self._h = C.c_void_p()
         o = BuildOpts()
         o.format = _FMT[fmt] if isinstance(fmt, str) else int(fmt)
         o.tm, o.tn, o.bw, o.n_sm, o.cmajor, o.nnz_limit = tm, tn, bw, n_sm, int(cmajor), nnz_limit
         o.row_begin, o.row_end = row_begin, row_end
+        o.tc_threshold, o.tc_width, o.tc_min_gain = tc_threshold, tc_width, tc_min_gain
         self.fmt = o.format
         self.row_begin = row_begin
         self.row_end = row_end if (row_begin or row_end) else dl.n
@@ -384,6 +398,19 @@ class Mat:
                     alpha_pillar_rowPtr=_np(a.alpha_pillar_rowPtr, a.n_segs + 1, np.uint32).copy(),
                     alpha_pillarIdx=_np(a.alpha_pillarIdx, a.n_sm + 2, np.uint32).copy(),
                     segVoMap=_np(a.segVoMap, R, np.uint32).copy())
+
+    def export_tcw(self):
+        a = TcwArrays()
+        _ck(lib().fx_tiles_export_tcw(self._h, C.byref(a)))
+        wn, rn = a.win_nnz, a.rest_nnz
+        return dict(n=a.n, nr=a.nr, npanel=a.npanel, W=a.W, T=a.T, min_gain=a.min_gain, ntc=a.ntc, dropped=a.dropped,
+                    win_nnz=wn, rest_nnz=rn,
+                    tc_cols=_np(a.tc_cols, a.npanel * a.W, np.int32).copy().reshape(a.npanel, a.W),
+                    tc_ncol=_np(a.tc_ncol, a.npanel, np.int32).copy(),
+                    win_cptr=_np(a.win_cptr, a.npanel * (a.W // 32) + 1, np.int32).copy(),
+                    win_code=_np(a.win_code, wn, np.uint16).copy(), win_val=_np(a.win_val, wn, np.float32).copy(),
+                    rest_rowptr=_np(a.rest_rowptr, a.n + 1, np.uint32).copy(),
+                    rest_col=_np(a.rest_col, rn, np.uint32).copy(), rest_val=_np(a.rest_val, rn, np.float32).copy())
 
     def spmm(self, B_ptr, C_ptr, k, stream=None, timed=False):
         """C = A*B on device pointers.  timed=True returns tElap in ms (events + sync)."""

@@ -31,6 +31,10 @@ int build_dispatch(fx_tiles* t, cudaStream_t s) {
   switch (t->format) {
     case FX_FMT_CSR: return FX_OK;
     case FX_FMT_ASPT: return fx::aspt_build(t, s);
+    case FX_FMT_TCW: {
+      int rc = fx::tcw_build(t, s);
+      return rc != FX_OK ? rc : fx::aspt_build(t, s);
+    }
     case FX_FMT_TILE: case FX_FMT_SEG: case FX_FMT_PILLAR: return fx::flex_build(t, s);
     default: fx::set_error("format %d not built by this entry point", t->format); return FX_ERR_UNSUPPORTED;
   }
@@ -65,7 +69,7 @@ extern "C" int fx_build(const fx_matrix* m, const fx_build_opts* opts, fx_tiles*
     fx::set_error("fx_build: event/stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(FX_ERR_CUDA);
   }
-  if (t->format == FX_FMT_ASPT) {
+  if (t->format == FX_FMT_ASPT || t->format == FX_FMT_TCW) {
     fx_aspt_dev& a = t->aspt;
     const int nloc = t->row_end - t->row_begin;
     a.n = nloc;
@@ -75,8 +79,18 @@ extern "C" int fx_build(const fx_matrix* m, const fx_build_opts* opts, fx_tiles*
     a.row0 = t->row_begin;
     a.BW = t->opts.bw ? t->opts.bw : (m->k >= 64 ? 128 : 256);  // sspmm_128.cu:34 vs sspmm_32.cu:33
     if (a.BW != 128 && a.BW != 256) { fx::set_error("bw must be 128 or 256"); return fail(FX_ERR_ARG); }
-    rc = fx::aspt_carve(t, m->n);
+    size_t extra = 0;
+    if (t->format == FX_FMT_TCW) {
+      fx_tcw_dev& w = t->tcw;
+      if (t->opts.tc_threshold) w.T = t->opts.tc_threshold;
+      if (t->opts.tc_width) w.W = t->opts.tc_width;
+      if (t->opts.tc_min_gain) w.min_gain = t->opts.tc_min_gain;
+      if (w.T < 2 || w.W < 32 || w.W > 4096 || w.W % 32) { fx::set_error("tc_threshold must be >= 2 and tc_width a multiple of 32 in [32,4096]"); return fail(FX_ERR_ARG); }
+      extra = fx::tcw_arena_bytes(t);
+    }
+    rc = fx::aspt_carve(t, m->n, extra);
     if (rc != FX_OK) return fail(rc);
+    if (t->format == FX_FMT_TCW && (rc = fx::tcw_carve(t)) != FX_OK) return fail(rc);
   } else if (t->format == FX_FMT_TILE || t->format == FX_FMT_SEG || t->format == FX_FMT_PILLAR) {
     rc = fx::flex_carve(t);
     if (rc != FX_OK) return fail(rc);
@@ -150,11 +164,12 @@ extern "C" int fx_tiles_export_aspt(fx_tiles* t, fx_aspt_arrays* o) {
 
 static int spmm_dispatch(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s) {
   const fx_matrix* m = t->mat;
-  if (t->format == FX_FMT_CSR || (k % 4 != 0 && t->format == FX_FMT_ASPT)) {
+  const bool tcw = t->format == FX_FMT_TCW;
+  if (t->format == FX_FMT_CSR || (k % 4 != 0 && (t->format == FX_FMT_ASPT || tcw)) || (tcw && k > t->k)) {
     // raw CSR over the shard's rows (run_ge_spmm path flex.cu:4285; "ssparse" regime :629)
     return fx::spmm_csr(m->rowptr_dev + t->row_begin, m->col_dev, m->val_dev, t->row_end - t->row_begin, B, C, k, s);
   }
-  if (t->format == FX_FMT_ASPT) return fx::spmm_aspt(t, B, C, k, s);
+  if (t->format == FX_FMT_ASPT || tcw) return fx::spmm_aspt(t, B, C, k, s);
   if (t->format == FX_FMT_TILE || t->format == FX_FMT_SEG || t->format == FX_FMT_PILLAR) return fx::flex_spmm(t, B, C, k, s);
   fx::set_error("fx_spmm: format %d has its own entry point", t->format);
   return FX_ERR_UNSUPPORTED;

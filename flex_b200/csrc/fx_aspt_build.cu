@@ -403,7 +403,7 @@ static int heavy_ctas(int npanel) {
   return npanel < g ? (npanel > 0 ? npanel : 1) : g;
 }
 
-int aspt_carve(fx_tiles* t, int64_t ncols) {
+int aspt_carve(fx_tiles* t, int64_t ncols, size_t extra_bytes) {
   fx_aspt_dev& a = t->aspt;
   const int64_t ne = a.ne, nr = a.nr, npanel = a.npanel;
   const int BW = a.BW, min_occ = BW * 3 / 4;
@@ -428,7 +428,7 @@ int aspt_carve(fx_tiles* t, int64_t ncols) {
   add(sizeof(int) * (size_t)a.special_cap * 2);
   add(sizeof(unsigned long long) * 8);
   add(sizeof(float) * a.partial_cap_floats);
-  int rc = t->arena.reserve(bytes);
+  int rc = t->arena.reserve(bytes + extra_bytes);
   if (rc != FX_OK) return rc;
   Arena& A = t->arena;
   a.csr_v = A.take<int>(nr + 2);
@@ -465,11 +465,13 @@ int aspt_build(fx_tiles* t, cudaStream_t s) {
   fx_aspt_dev& a = t->aspt;
   const fx_matrix* m = t->mat;
   const int BW = a.BW, min_occ = BW * 3 / 4;
-  const uint32_t* col = m->col_dev + m->rowptr[t->row_begin];
-  const float* val = m->val_dev + m->rowptr[t->row_begin];
+  const uint32_t* col = t->src_rowptr ? t->src_col : m->col_dev + m->rowptr[t->row_begin];
+  const float* val = t->src_rowptr ? t->src_val : m->val_dev + m->rowptr[t->row_begin];
+  const uint32_t* src_rowptr = t->src_rowptr ? t->src_rowptr : m->rowptr_dev;
+  const int src_row0 = t->src_rowptr ? t->src_row0 : t->row_begin;
   const int nloc = t->row_end - t->row_begin;
   FX_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(unsigned long long) * 8, s));
-  k_pad_rowptr<<<ceil_div(a.nr + 1, 256), 256, 0, s>>>(m->rowptr_dev, t->row_begin, nloc, a.nr, a.ne, a.csr_v);
+  k_pad_rowptr<<<ceil_div(a.nr + 1, 256), 256, 0, s>>>(src_rowptr, src_row0, nloc, a.nr, a.ne, a.csr_v);
   FX_LAUNCH_CHECK();
   k_detect<<<a.npanel, 256, 0, s>>>(a.csr_v, col, min_occ, a.mcsr_chk, a.stats);
   FX_LAUNCH_CHECK();

@@ -127,8 +127,30 @@ struct fx_aspt_dev {  // device-side ASpT format (aspt/sspmm_128.cu:76-90 global
   const float* csr_ev_use = nullptr;
 };
 
+struct fx_tcw_dev {  // tensor-window format (fx_tcw_build.cu): per-panel column lists + window nz + remainder CSR
+  int T = 4, W = 512, min_gain = 64;
+  int *tc_cols = nullptr, *tc_ncol = nullptr, *tc_slot = nullptr, *tc_panels = nullptr;
+  int *csr_v = nullptr, *win_len = nullptr, *win_rowptr = nullptr, *chunk_len = nullptr, *win_cptr = nullptr;
+  uint32_t *rest_rowptr = nullptr, *rest_col = nullptr;
+  uint16_t* win_code = nullptr;
+  float *win_val = nullptr, *rest_val = nullptr;
+  float* tc_out = nullptr;  // [ntc][128][k] products of the window parts
+  unsigned long long* stats = nullptr;
+  long long win_nnz = 0, ncols_listed = 0;
+  int ntc = 0, dropped = 0;
+  std::vector<int32_t> h_cols, h_ncol, h_win_cptr;
+  std::vector<uint16_t> h_win_code;
+  std::vector<uint32_t> h_rest_rowptr, h_rest_col;
+  std::vector<float> h_win_val, h_rest_val;
+};
+
 struct fx_tiles {
   const fx_matrix* mat = nullptr;
+  // CSR the ASpT builder reads; null = the matrix itself (FX_FMT_TCW points it at the remainder)
+  const uint32_t *src_rowptr = nullptr, *src_col = nullptr;
+  const float* src_val = nullptr;
+  int src_row0 = 0;
+  fx_tcw_dev tcw;
   fx_build_opts opts{};
   int format = FX_FMT_ASPT;
   int k = 0;
@@ -153,8 +175,12 @@ namespace fx {
 int ensure_device(const fx_matrix* m);
 // fx_aspt_build.cu
 size_t aspt_arena_bytes(int64_t n_rows, int64_t ncols, int64_t ne, int BW, int k, int G);
-int aspt_carve(fx_tiles* t, int64_t ncols);
+int aspt_carve(fx_tiles* t, int64_t ncols, size_t extra_bytes = 0);
 int aspt_build(fx_tiles* t, cudaStream_t s);
+// fx_tcw_build.cu
+size_t tcw_arena_bytes(const fx_tiles* t);
+int tcw_carve(fx_tiles* t);
+int tcw_build(fx_tiles* t, cudaStream_t s);
 // fx_flex_build.cu
 int flex_carve(fx_tiles* t);
 int flex_build(fx_tiles* t, cudaStream_t s);

@@ -14,6 +14,7 @@
 #include <cooperative_groups.h>
 
 #include "fx_common.cuh"
+#include "fx_tc_kernel.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -107,6 +108,9 @@ struct PanelArgs {
   float* C;
   int npanel, nloc, k, BW, TS;
   int split;  // CTAs per panel (>1 when the shard has too few panels to fill the GPU); cut at row boundaries
+  // FX_FMT_TCW: products of the panels' tensor windows, added when a row is stored
+  const float* tc_out;  // [ntc][128][k]
+  const int* tc_slot;   // [npanel] position in tc_out or -1; nullptr = no windows
 };
 
 // ---- long-row chunks: partial[i,:] = sum over the i-th 512-nz chunk --------------------------
@@ -272,6 +276,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_panel(PanelArgs a, co
       for (int c = 0; c < nch; ++c) {
         const float4 pp = P4[(size_t)c * k4];
         acc.x += pp.x; acc.y += pp.y; acc.z += pp.z; acc.w += pp.w;
+      }
+    }
+    if (a.tc_slot) {
+      const int ts = a.tc_slot[p];
+      if (ts >= 0) {
+        const float4 tt = ldg4(reinterpret_cast<const float4*>(a.tc_out) + ((size_t)ts * BH + r) * k4 + c4);
+        acc.x += tt.x; acc.y += tt.y; acc.z += tt.z; acc.w += tt.w;
       }
     }
     if (col_ok && row < a.nloc) C4[(size_t)row * k4] = acc;
@@ -578,11 +589,36 @@ static int launch_aspt(const fx_tiles* t, const PanelArgs& a, int special_p, cud
   }
 }
 
+template <int N>
+static int launch_tc(const fxtc::TcArgs& ta, int ntc, cudaStream_t s) {
+  const size_t smem = fxtc::tc_smem_bytes<N>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    FX_CUDA(cudaFuncSetAttribute(fxtc::k_spmm_tc<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(ntc, ceil_div(ta.k, N));
+  fxtc::k_spmm_tc<N><<<grid, 256, smem, s>>>(ta);
+  FX_LAUNCH_CHECK();
+  return FX_OK;
+}
+
 int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s) {
   const fx_aspt_dev& d = t->aspt;
   if (d.npanel == 0) return FX_OK;
   const int KC = pick_kc(k);
   PanelArgs a;
+  a.tc_out = nullptr; a.tc_slot = nullptr;
+  if (t->format == FX_FMT_TCW && t->tcw.ntc > 0) {  // tensor windows first; the panel kernel adds them in
+    const fx_tcw_dev& w = t->tcw;
+    fxtc::TcArgs ta;
+    ta.win_cptr = w.win_cptr; ta.win_code = w.win_code; ta.win_val = w.win_val;
+    ta.tc_panels = w.tc_panels; ta.tc_cols = w.tc_cols; ta.tc_ncol = w.tc_ncol;
+    ta.B = B; ta.out = w.tc_out; ta.k = k; ta.W = w.W;
+    const int rc = KC == 32 ? launch_tc<32>(ta, w.ntc, s) : (KC == 64 ? launch_tc<64>(ta, w.ntc, s) : launch_tc<128>(ta, w.ntc, s));
+    if (rc != FX_OK) return rc;
+    a.tc_out = w.tc_out; a.tc_slot = w.tc_slot;
+  }
   a.mcsr_cnt = d.mcsr_cnt; a.mcsr_e = d.mcsr_e_use; a.mcsr_list = d.mcsr_list;
   a.csr_e = d.csr_e_use; a.csr_ev = d.csr_ev_use;
   static const bool no_special = getenv("FLEX_NO_SPECIAL") != nullptr;

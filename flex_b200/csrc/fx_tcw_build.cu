@@ -1,0 +1,461 @@
+// fx_tcw_build.cu -- builder of the tensor-window format (FX_FMT_TCW): the B200-native tile format.
+//
+// Flex's thesis (mat.cu:1345-1518 tiles, :718-1050 diagonal tiling) is that after reordering many
+// rows of a panel share columns, and that those shared columns should be served from on-chip memory
+// once per panel.  On a B200 the on-chip consumer of choice is the tensor core, so the format is:
+//   per 128-row panel p : S_p = the (at most W) columns with the most nz in the panel, each with
+//                         at least T of them, ascending                      -> tc_cols / tc_ncol
+//   window part         : the nz whose column is in S_p, grouped by (panel, 32-column chunk of S_p) and
+//                         ordered by (row, slot) inside a chunk, as (row-in-panel<<5 | slot&31, value):
+//                         one chunk is one K=32 step of the tensor kernel, which scatters its entries with
+//                         all threads at once                                -> win_cptr/code/val
+//   remainder           : every other nz as an ordinary CSR                  -> rest_rowptr/col/val
+// The remainder then goes through the ASpT builder unchanged (fx_aspt_build.cu), the window part is
+// multiplied by k_spmm_tc (fx_tc_kernel.cuh).  oracle/fx_oracle_tcw.c restates the selection rule
+// on the CPU; tests compare every array bit for bit.
+//
+// Selection rule (deterministic):  cnt_p[c] = nz of panel p in column c;  candidates = {c : cnt >= T'}
+// where T' = T, doubled until at most CAND_CAP candidates remain (at most 6 doublings, else the
+// panel gets no window);  order candidates by (cnt descending, column ascending), keep the first
+// min(W, #candidates);  the panel keeps its window only if  sum(cnt) - #kept >= MIN_GAIN  (B-row
+// fetches saved).  Kept columns are listed ascending.
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+#include <cooperative_groups/scan.h>
+
+#include "fx_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int BH = 128;
+constexpr int CAND_CAP = 8192;
+constexpr unsigned CNT_MASK = 0xFFFFFFu;
+constexpr unsigned MARK = 0x80000000u;
+constexpr int MAX_CH = 128;  // W <= 4096
+
+__device__ __forceinline__ void cmpswap64(unsigned long long& a, unsigned long long& b) {
+  if (a > b) { unsigned long long t = a; a = b; b = t; }
+}
+
+// normalised bitonic network over shared memory (every comparator moves the minimum down, so slots
+// >= n act as +inf padding and any n sorts correctly)
+__device__ void tcw_sort_u64(unsigned long long* a, int n) {
+  int N = 1;
+  while (N < n) N <<= 1;
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      int j = i ^ (k - 1);
+      if (j > i && j < n) cmpswap64(a[i], a[j]);
+    }
+    __syncthreads();
+    for (int s = k >> 2; s > 0; s >>= 1) {
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        int j = i ^ s;
+        if (j > i && j < n) cmpswap64(a[i], a[j]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void k_tcw_pad(const uint32_t* __restrict__ rowptr, int row0, int nloc, int nr, int ne, int* __restrict__ csr_v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= nr) csr_v[i] = i <= nloc ? (int)(rowptr[row0 + i] - rowptr[row0]) : ne;
+}
+
+// stats: [0] window nz, [1] listed columns, [2] panels with a window, [3] panels dropped by the cap
+__global__ void __launch_bounds__(512) k_tcw_select(const int* __restrict__ csr_v, const uint32_t* __restrict__ col, int npanel,
+                                                    int ncols, int T, int W, int min_gain, unsigned* __restrict__ cnt_all,
+                                                    int* __restrict__ tc_cols, int* __restrict__ tc_ncol,
+                                                    int* __restrict__ win_len, int* __restrict__ chunk_len,
+                                                    unsigned long long* __restrict__ stats) {
+  extern __shared__ unsigned long long skeys[];  // CAND_CAP
+  __shared__ int s_nc;
+  __shared__ int hist[MAX_CH];
+  const int CH = W / 32;
+  __shared__ long long s_sum;
+  unsigned* cnt = cnt_all + (size_t)blockIdx.x * ncols;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int p = blockIdx.x; p < npanel; p += gridDim.x) {
+    const int lb = csr_v[p * BH], ub = csr_v[(p + 1) * BH];
+    if (threadIdx.x == 0) { s_nc = 0; s_sum = 0; }
+    __syncthreads();
+    // pass 1: count; the T-th hit of a column registers it
+    for (int e = lb + threadIdx.x; e < ub; e += blockDim.x) {
+      const unsigned c = col[e];
+      const unsigned old = atomicAdd(&cnt[c], 1u);
+      if ((int)old == T - 1) {
+        const int pos = atomicAdd(&s_nc, 1);
+        if (pos < CAND_CAP) skeys[pos] = c;
+      }
+    }
+    __syncthreads();
+    int nc = s_nc;
+    int Tcur = T;
+    for (int round = 0; nc > CAND_CAP && round < 6; ++round) {  // too many candidates: double the bar
+      Tcur *= 2;
+      __syncthreads();
+      if (threadIdx.x == 0) s_nc = 0;
+      __syncthreads();
+      const unsigned bit = 1u << (24 + round);
+      for (int e = lb + threadIdx.x; e < ub; e += blockDim.x) {
+        const unsigned c = col[e];
+        if ((int)(cnt[c] & CNT_MASK) >= Tcur) {
+          const unsigned old = atomicOr(&cnt[c], bit);
+          if (!(old & bit)) {
+            const int pos = atomicAdd(&s_nc, 1);
+            if (pos < CAND_CAP) skeys[pos] = c;
+          }
+        }
+      }
+      __syncthreads();
+      nc = s_nc;
+    }
+    int ns = 0;
+    if (nc > 0 && nc <= CAND_CAP) {
+      for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+        const unsigned c = (unsigned)skeys[i];
+        skeys[i] = ((unsigned long long)(0xFFFFFFFFu - (cnt[c] & CNT_MASK)) << 32) | c;
+      }
+      __syncthreads();
+      tcw_sort_u64(skeys, nc);
+      ns = nc < W ? nc : W;
+      long long part = 0;
+      for (int i = threadIdx.x; i < ns; i += blockDim.x) part += (long long)(0xFFFFFFFFu - (unsigned)(skeys[i] >> 32));
+      part = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), part, cg::plus<long long>());
+      if (lane == 0 && part) atomicAdd((unsigned long long*)&s_sum, (unsigned long long)part);
+      __syncthreads();
+      const long long captured = s_sum;
+      if (captured - ns < min_gain) ns = 0;
+      __syncthreads();
+      if (ns > 0) {
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) skeys[i] &= 0xFFFFFFFFull;  // keep the column only
+        __syncthreads();
+        tcw_sort_u64(skeys, ns);
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) cnt[(unsigned)skeys[i]] = MARK | (unsigned)i;
+        if (threadIdx.x == 0) {
+          atomicAdd(&stats[0], (unsigned long long)captured);
+          atomicAdd(&stats[1], (unsigned long long)ns);
+          atomicAdd(&stats[2], 1ull);
+        }
+      }
+    } else if (nc > CAND_CAP && threadIdx.x == 0) {
+      atomicAdd(&stats[3], 1ull);
+    }
+    for (int i = threadIdx.x; i < W; i += blockDim.x) tc_cols[(size_t)p * W + i] = i < ns ? (int)(unsigned)skeys[i] : -1;
+    if (threadIdx.x == 0) tc_ncol[p] = ns;
+    for (int i = threadIdx.x; i < CH; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    // pass 2: window nz of every row and of every 32-column chunk of the list
+    for (int r = warp; r < BH; r += nwarp) {
+      int n = 0;
+      if (ns > 0) {
+        const int lo = csr_v[p * BH + r], hi = csr_v[p * BH + r + 1];
+        for (int e = lo + lane; e < hi; e += 32) {
+          const unsigned f = cnt[col[e]];
+          if (f >> 31) { ++n; atomicAdd(&hist[(f & 0xFFFFu) >> 5], 1); }
+        }
+        n = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), n, cg::plus<int>());
+      }
+      if (lane == 0) win_len[p * BH + r] = n;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CH; i += blockDim.x) chunk_len[(size_t)p * CH + i] = hist[i];
+    // pass 3: leave the counters zeroed
+    for (int e = lb + threadIdx.x; e < ub; e += blockDim.x) cnt[col[e]] = 0u;
+    __syncthreads();
+  }
+}
+
+// exclusive scan by one CTA: out[n] = total
+__global__ void __launch_bounds__(1024) k_tcw_scan(const int* __restrict__ in, int n, int* __restrict__ out) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  auto warp = cg::tiled_partition<32>(cg::this_thread_block());
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? in[i] : 0;
+    const int inc = cg::inclusive_scan(warp, v);
+    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int ws = warp_sum[threadIdx.x];
+      const int wi = cg::inclusive_scan(warp, ws);
+      warp_sum[threadIdx.x] = wi - ws;
+    }
+    __syncthreads();
+    const int incl = carry_s + warp_sum[threadIdx.x >> 5] + inc;
+    if (i < n) out[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+__global__ void k_tcw_rowptr(const int* __restrict__ csr_v, const int* __restrict__ win_rowptr, int nloc,
+                             uint32_t* __restrict__ rest_rowptr) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= nloc) rest_rowptr[i] = (uint32_t)(csr_v[i] - win_rowptr[i]);
+}
+
+// ascending list of the panels that have a window; tc_slot[p] = position in that list or -1
+__global__ void __launch_bounds__(1024) k_tcw_panels(const int* __restrict__ tc_ncol, int npanel, int* __restrict__ tc_panels,
+                                                     int* __restrict__ tc_slot, int* __restrict__ ntc) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  auto warp = cg::tiled_partition<32>(cg::this_thread_block());
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < npanel; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = (i < npanel && tc_ncol[i] > 0) ? 1 : 0;
+    const int inc = cg::inclusive_scan(warp, v);
+    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int ws = warp_sum[threadIdx.x];
+      const int wi = cg::inclusive_scan(warp, ws);
+      warp_sum[threadIdx.x] = wi - ws;
+    }
+    __syncthreads();
+    const int incl = carry_s + warp_sum[threadIdx.x >> 5] + inc;
+    if (i < npanel) {
+      tc_slot[i] = v ? incl - 1 : -1;
+      if (v) tc_panels[incl - 1] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *ntc = carry_s;
+}
+
+// split of every row into its window part (chunk-major inside the panel) and its remainder (row order)
+__global__ void __launch_bounds__(512) k_tcw_split(const int* __restrict__ csr_v, const uint32_t* __restrict__ col,
+                                                   const float* __restrict__ val, const int* __restrict__ win_rowptr,
+                                                   const int* __restrict__ win_cptr, const int* __restrict__ tc_cols,
+                                                   const int* __restrict__ tc_ncol, int npanel, int ncols, int W,
+                                                   unsigned* __restrict__ cnt_all, uint16_t* __restrict__ win_code,
+                                                   float* __restrict__ win_val, uint32_t* __restrict__ rest_col,
+                                                   float* __restrict__ rest_val) {
+  extern __shared__ int off2[];  // [CH][128] nz of (chunk, row), then their exclusive scan
+  __shared__ int wsum[16];
+  unsigned* cnt = cnt_all + (size_t)blockIdx.x * ncols;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const int CH = W / 32, n2 = CH * BH;
+  for (int p = blockIdx.x; p < npanel; p += gridDim.x) {
+    const int ns = tc_ncol[p];
+    const int* list = tc_cols + (size_t)p * W;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) cnt[list[i]] = MARK | (unsigned)i;
+    if (ns > 0) for (int i = threadIdx.x; i < n2; i += blockDim.x) off2[i] = 0;
+    __syncthreads();
+    if (ns > 0) {
+      for (int r = warp; r < BH; r += nwarp) {
+        const int lo = csr_v[p * BH + r], hi = csr_v[p * BH + r + 1];
+        for (int e = lo + lane; e < hi; e += 32) {
+          const unsigned f = cnt[col[e]];
+          if (f >> 31) atomicAdd(&off2[((f & 0xFFFFu) >> 5) * BH + r], 1);
+        }
+      }
+      __syncthreads();
+      // exclusive scan of off2 in (chunk, row) order
+      const int ipt = (n2 + (int)blockDim.x - 1) / (int)blockDim.x;
+      const int b = threadIdx.x * ipt, e = min(n2, b + ipt);
+      int sum = 0;
+      for (int i = b; i < e; ++i) sum += off2[i];
+      auto w32 = cg::tiled_partition<32>(cg::this_thread_block());
+      const int inc = cg::inclusive_scan(w32, sum);
+      if (lane == 31) wsum[warp] = inc;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        const int ws = threadIdx.x < nwarp ? wsum[threadIdx.x] : 0;
+        const int wi = cg::inclusive_scan(w32, ws);
+        if (threadIdx.x < nwarp) wsum[threadIdx.x] = wi - ws;
+      }
+      __syncthreads();
+      int run = wsum[warp] + inc - sum;
+      for (int i = b; i < e; ++i) { const int v = off2[i]; off2[i] = run; run += v; }
+      __syncthreads();
+    }
+    const int wbase = win_cptr[(size_t)p * CH];
+    for (int r = warp; r < BH; r += nwarp) {
+      const int row = p * BH + r;
+      const int lo = csr_v[row], hi = csr_v[row + 1];
+      int ro = lo - win_rowptr[row];
+      int last_ch = -1, last_cnt = 0;
+      for (int e0 = lo; e0 < hi; e0 += 32) {
+        const int e = e0 + lane;
+        const bool valid = e < hi;
+        unsigned c = 0, f = 0;
+        float v = 0.f;
+        if (valid) { c = col[e]; v = val[e]; f = ns > 0 ? cnt[c] : 0u; }
+        const bool isw = (f >> 31) != 0u;
+        const unsigned mw = __ballot_sync(0xffffffffu, isw), mr = __ballot_sync(0xffffffffu, valid && !isw);
+        int ch = -1, pc = 0;
+        if (isw) {
+          const int s = (int)(f & 0xFFFFu);
+          ch = s >> 5;
+          const unsigned peers = __match_any_sync(mw, ch);
+          pc = __popc(peers);
+          const int rank = __popc(peers & lt) + (ch == last_ch ? last_cnt : 0);
+          const int pos = wbase + off2[ch * BH + r] + rank;
+          win_code[pos] = (uint16_t)((r << 5) | (s & 31));
+          win_val[pos] = v;
+        } else if (valid) {
+          const int pos = ro + __popc(mr & lt);
+          rest_col[pos] = c;
+          rest_val[pos] = v;
+        }
+        ro += __popc(mr);
+        if (mw) {  // nz are in ascending slot order: only the last chunk of this batch can continue
+          const int hl = 31 - __clz(mw);
+          const int ch_h = __shfl_sync(0xffffffffu, ch, hl), pc_h = __shfl_sync(0xffffffffu, pc, hl);
+          last_cnt = (ch_h == last_ch ? last_cnt : 0) + pc_h;
+          last_ch = ch_h;
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) cnt[list[i]] = 0u;
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+namespace fx {
+
+size_t tcw_arena_bytes(const fx_tiles* t) {
+  const fx_aspt_dev& a = t->aspt;
+  const fx_tcw_dev& w = t->tcw;
+  const int64_t ne = t->nnz_local, nr = a.nr, npanel = a.npanel;
+  size_t bytes = 0;
+  auto add = [&](size_t b) { bytes += Arena::pad(b) + 256; };
+  add(sizeof(int) * (size_t)npanel * w.W);
+  for (int i = 0; i < 3; ++i) add(sizeof(int) * (npanel + 2));
+  for (int i = 0; i < 4; ++i) add(sizeof(int) * (nr + 2));
+  for (int i = 0; i < 2; ++i) add(sizeof(int) * ((size_t)npanel * (w.W / 32) + 2));
+  add(sizeof(uint16_t) * (ne + 2));
+  add(sizeof(float) * (ne + 2) * 2);
+  add(sizeof(uint32_t) * (ne + 2));
+  add(sizeof(float) * (size_t)nr * t->k);
+  add(sizeof(unsigned long long) * 8);
+  return bytes;
+}
+
+int tcw_carve(fx_tiles* t) {
+  const fx_aspt_dev& a = t->aspt;
+  fx_tcw_dev& w = t->tcw;
+  const int64_t ne = t->nnz_local, nr = a.nr, npanel = a.npanel;
+  Arena& A = t->arena;
+  w.tc_cols = A.take<int>((size_t)npanel * w.W);
+  w.tc_ncol = A.take<int>(npanel + 2);
+  w.tc_slot = A.take<int>(npanel + 2);
+  w.tc_panels = A.take<int>(npanel + 2);
+  w.csr_v = A.take<int>(nr + 2);
+  w.win_len = A.take<int>(nr + 2);
+  w.win_rowptr = A.take<int>(nr + 2);
+  w.rest_rowptr = A.take<uint32_t>(nr + 2);
+  w.chunk_len = A.take<int>((size_t)npanel * (w.W / 32) + 2);
+  w.win_cptr = A.take<int>((size_t)npanel * (w.W / 32) + 2);
+  w.win_code = A.take<uint16_t>(ne + 2);
+  w.win_val = A.take<float>(ne + 2);
+  w.rest_val = A.take<float>(ne + 2);
+  w.rest_col = A.take<uint32_t>(ne + 2);
+  w.tc_out = A.take<float>((size_t)nr * t->k);
+  w.stats = A.take<unsigned long long>(8);
+  if (!w.stats || !w.tc_out) { set_error("tcw arena carve overflow"); return FX_ERR_NOMEM; }
+  return FX_OK;
+}
+
+// Runs in front of aspt_build inside the timed region of fx_build.
+int tcw_build(fx_tiles* t, cudaStream_t s) {
+  fx_aspt_dev& a = t->aspt;
+  fx_tcw_dev& w = t->tcw;
+  const fx_matrix* m = t->mat;
+  const int nloc = t->row_end - t->row_begin;
+  const int ne = (int)t->nnz_local;
+  const uint32_t* col = m->col_dev + m->rowptr[t->row_begin];
+  const float* val = m->val_dev + m->rowptr[t->row_begin];
+  FX_CUDA(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * 8, s));
+  k_tcw_pad<<<ceil_div(a.nr + 1, 256), 256, 0, s>>>(m->rowptr_dev, t->row_begin, nloc, a.nr, ne, w.csr_v);
+  FX_LAUNCH_CHECK();
+  static bool attr_set = false;
+  if (!attr_set) {
+    FX_CUDA(cudaFuncSetAttribute(k_tcw_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_CAP * sizeof(unsigned long long))));
+    attr_set = true;
+  }
+  k_tcw_select<<<a.G, 512, CAND_CAP * sizeof(unsigned long long), s>>>(w.csr_v, col, a.npanel, (int)m->n, w.T, w.W, w.min_gain,
+                                                                      a.cnt_scratch, w.tc_cols, w.tc_ncol, w.win_len, w.chunk_len, w.stats);
+  FX_LAUNCH_CHECK();
+  k_tcw_scan<<<1, 1024, 0, s>>>(w.win_len, a.nr, w.win_rowptr);
+  FX_LAUNCH_CHECK();
+  k_tcw_scan<<<1, 1024, 0, s>>>(w.chunk_len, a.npanel * (w.W / 32), w.win_cptr);
+  FX_LAUNCH_CHECK();
+  k_tcw_rowptr<<<ceil_div(nloc + 1, 256), 256, 0, s>>>(w.csr_v, w.win_rowptr, nloc, w.rest_rowptr);
+  FX_LAUNCH_CHECK();
+  k_tcw_panels<<<1, 1024, 0, s>>>(w.tc_ncol, a.npanel, w.tc_panels, w.tc_slot, reinterpret_cast<int*>(w.stats + 4));
+  FX_LAUNCH_CHECK();
+  const size_t split_smem = sizeof(int) * (size_t)(w.W / 32) * BH;
+  static size_t split_set = 0;
+  if (split_smem > 48 * 1024 && split_smem > split_set) {
+    FX_CUDA(cudaFuncSetAttribute(k_tcw_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem));
+    split_set = split_smem;
+  }
+  k_tcw_split<<<a.G, 512, split_smem, s>>>(w.csr_v, col, val, w.win_rowptr, w.win_cptr, w.tc_cols, w.tc_ncol, a.npanel, (int)m->n,
+                                           w.W, a.cnt_scratch, w.win_code, w.win_val, w.rest_col, w.rest_val);
+  FX_LAUNCH_CHECK();
+  FX_CUDA(cudaMemcpyAsync(t->stats_host, w.stats, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
+  FX_CUDA(cudaStreamSynchronize(s));
+  w.win_nnz = (long long)t->stats_host[0];
+  w.ncols_listed = (long long)t->stats_host[1];
+  w.ntc = (int)t->stats_host[2];
+  w.dropped = (int)t->stats_host[3];
+  // the remainder is what the ASpT builder sees
+  t->src_rowptr = w.rest_rowptr;
+  t->src_row0 = 0;
+  t->src_col = w.rest_col;
+  t->src_val = w.rest_val;
+  a.ne = ne - (int)w.win_nnz;
+  return FX_OK;
+}
+
+}  // namespace fx
+
+template <class T>
+static int tcw_d2h(std::vector<T>& dst, const void* src, size_t count) {
+  dst.resize(count);
+  if (count) FX_CUDA(cudaMemcpy(dst.data(), src, sizeof(T) * count, cudaMemcpyDeviceToHost));
+  return FX_OK;
+}
+
+extern "C" int fx_tiles_export_tcw(fx_tiles* t, fx_tcw_arrays* o) {
+  FX_REQUIRE(t && o && t->format == FX_FMT_TCW, FX_ERR_ARG, "fx_tiles_export_tcw: not a tensor-window handle");
+  fx_tcw_dev& w = t->tcw;
+  const fx_aspt_dev& a = t->aspt;
+  FX_CUDA(cudaDeviceSynchronize());
+  const int nloc = t->row_end - t->row_begin;
+  const size_t rest = (size_t)(t->nnz_local - w.win_nnz);
+  int rc;
+  if ((rc = tcw_d2h(w.h_cols, w.tc_cols, (size_t)a.npanel * w.W))) return rc;
+  if ((rc = tcw_d2h(w.h_ncol, w.tc_ncol, a.npanel))) return rc;
+  if ((rc = tcw_d2h(w.h_win_cptr, w.win_cptr, (size_t)a.npanel * (w.W / 32) + 1))) return rc;
+  if ((rc = tcw_d2h(w.h_win_code, w.win_code, (size_t)w.win_nnz))) return rc;
+  if ((rc = tcw_d2h(w.h_win_val, w.win_val, (size_t)w.win_nnz))) return rc;
+  if ((rc = tcw_d2h(w.h_rest_rowptr, w.rest_rowptr, (size_t)nloc + 1))) return rc;
+  if ((rc = tcw_d2h(w.h_rest_col, w.rest_col, rest))) return rc;
+  if ((rc = tcw_d2h(w.h_rest_val, w.rest_val, rest))) return rc;
+  o->n = nloc; o->nr = a.nr; o->npanel = a.npanel; o->W = w.W; o->T = w.T; o->min_gain = w.min_gain;
+  o->ntc = w.ntc; o->dropped = w.dropped;
+  o->win_nnz = w.win_nnz; o->rest_nnz = (int64_t)rest;
+  o->tc_cols = w.h_cols.data(); o->tc_ncol = w.h_ncol.data(); o->win_cptr = w.h_win_cptr.data();
+  o->win_code = w.h_win_code.data(); o->win_val = w.h_win_val.data();
+  o->rest_rowptr = w.h_rest_rowptr.data(); o->rest_col = w.h_rest_col.data(); o->rest_val = w.h_rest_val.data();
+  return FX_OK;
+}

@@ -43,7 +43,10 @@ typedef enum {
   FX_FMT_ASPT = 1,   /* ASpT dense/sparse tiles  aspt/sspmm_128.cu:831-1087,1207-1333 */
   FX_FMT_TILE = 2,   /* Flex tile format         mat.cu:1345-1518 */
   FX_FMT_SEG = 3,    /* Flex tile-segment format mat.cu:1192-1269 + SM buckets :1097-1162 */
-  FX_FMT_PILLAR = 4  /* Flex diagonal tiling     mat.cu:680-942 */
+  FX_FMT_PILLAR = 4, /* Flex diagonal tiling     mat.cu:680-942 */
+  FX_FMT_TCW = 5     /* B200-native: per-panel tensor-core windows (the panel's most shared columns, multiplied
+                        by tcgen05) + ASpT over the remaining nz.  Serves the same purpose as the reference's
+                        on-chip tiles (mat.cu:1345-1518, aspt dense tiles); no reference counterpart layout. */
 } fx_format;
 
 typedef struct fx_matrix fx_matrix; /* replaces class DataLoader (DataLoader.cuh:21-112) */
@@ -66,7 +69,10 @@ typedef struct {
   int32_t n_sm;       /* SM count for F4/F5 bucketing, 0 = device value */
   int32_t row_begin, row_end; /* build only rows [row_begin,row_end) (row-panel shard); 0,0 = all */
   int32_t cmajor;     /* FX_FMT_TILE: 0 = csr2flex_Rmajor, 1 = csr2flex_Cmajor (COL_MAJ_TILE, DataLoader.cuh:18) */
-  int32_t reserved[7];
+  int32_t tc_threshold; /* FX_FMT_TCW: a column joins a panel's tensor window with >= this many nz in the panel (0 = 4) */
+  int32_t tc_width;     /* FX_FMT_TCW: at most this many window columns per panel (0 = 512) */
+  int32_t tc_min_gain;  /* FX_FMT_TCW: a panel keeps its window only if it saves >= this many B-row fetches (0 = 64) */
+  int32_t reserved[4];
 } fx_build_opts;
 
 typedef struct { /* ASpT metadata export for bit-exact checks; pointers are host copies
@@ -106,6 +112,19 @@ typedef struct { /* diagonal tiling / pillar format (mat.cu:680-903; Mat_POD mat
   const float *alpha_vals;
   float empty_wp_p, band_nz_p;
 } fx_pillar_arrays;
+
+typedef struct { /* tensor-window format (FX_FMT_TCW), host copies owned by the handle */
+  int32_t n, nr, npanel, W, T, min_gain, ntc, dropped;
+  int64_t win_nnz, rest_nnz;
+  const int32_t *tc_cols;     /* npanel*W : ascending column list of each panel, -1 padded (W a multiple of 32) */
+  const int32_t *tc_ncol;     /* npanel */
+  const int32_t *win_cptr;    /* npanel*(W/32)+1 : window nz of each (panel, 32-column chunk of its list) */
+  const uint16_t *win_code;   /* win_nnz : (row in panel << 5) | (list position & 31), (row, position) order in a chunk */
+  const float *win_val;       /* win_nnz */
+  const uint32_t *rest_rowptr; /* n+1 */
+  const uint32_t *rest_col;    /* rest_nnz */
+  const float *rest_val;       /* rest_nnz */
+} fx_tcw_arrays;
 
 typedef struct { /* what run()/process() print: flex.cu:5134-5631, aspt/sspmm_128.cu:1406-1446 */
   float tPre_ms, tElap_ms;
@@ -175,6 +194,7 @@ int fx_tiles_export_aspt(fx_tiles *t, fx_aspt_arrays *out);
 int fx_tiles_export_tile(fx_tiles *t, fx_tile_arrays *out);
 int fx_tiles_export_seg(fx_tiles *t, fx_seg_arrays *out);
 int fx_tiles_export_pillar(fx_tiles *t, fx_pillar_arrays *out);
+int fx_tiles_export_tcw(fx_tiles *t, fx_tcw_arrays *out);
 void fx_tiles_free(fx_tiles *t); /* Mat::freeMatGPU* mat.cuh:184-220 */
 
 /* ---- L3: SpMM ---------------------------------------------------------------------- */

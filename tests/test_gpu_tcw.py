@@ -1,0 +1,117 @@
+"""GPU parity tests of the tensor-window format (FX_FMT_TCW): the plan bit for bit against its CPU
+restatement (oracle/tcw.py), the SpMM (tcgen05 window kernel + ASpT remainder) against the
+reference-pinned SpMM oracle within the repo's row-normwise 1e-5 contract."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import flex_b200 as fx
+from util import random_csr, rand_dense
+from test_gpu_spmm import run_spmm, assert_close
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+import tcw as tcw_oracle  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+ARRAYS = ("tc_cols", "tc_ncol", "win_cptr", "win_code", "win_val", "rest_rowptr", "rest_col", "rest_val")
+
+
+def assert_plan_equal(mat, rp, c, v, **kw):
+    e = mat.export_tcw()
+    o = tcw_oracle.plan(rp, c, v, **kw)
+    for f in ("n", "nr", "npanel", "W", "T", "ntc", "win_nnz", "rest_nnz"):
+        assert e[f] == o[f], (f, e[f], o[f])
+    for f in ARRAYS:
+        assert np.array_equal(e[f], o[f]), f
+    return o
+
+
+@pytest.mark.parametrize("k", [32, 64, 128, 256])
+def test_planted_blocks(orc, k):
+    n = 1500
+    rp, c, v = random_csr(n, 6, 21, hubs=2, blocks=8)
+    dl = fx.DataLoader.from_arrays(rp, c, v, k)
+    B = rand_dense(n, k, 3)
+    gold = orc.spmm_ref(rp, c, v, B)
+    mat = fx.Mat(dl, fmt="tcw")
+    o = assert_plan_equal(mat, rp, c, v)
+    assert o["ntc"] > 0 and o["win_nnz"] > 0
+    rp2, c2, v2 = tcw_oracle.reassemble(o)
+    assert np.array_equal(rp2, rp.astype(np.int64)) and np.array_equal(c2, c.astype(np.int64)) and np.array_equal(v2, v)
+    res = run_spmm(mat, B, n)
+    assert_close(orc, gold, res, rp)
+    mat.free()
+
+
+@pytest.mark.parametrize("T,W,min_gain", [(2, 64, 1), (3, 32, 16), (8, 1024, 64), (4, 512, 100000)])
+def test_plan_parameters(orc, T, W, min_gain):
+    n, k = 1100, 64
+    rp, c, v = random_csr(n, 9, 5, hubs=1, blocks=6)
+    dl = fx.DataLoader.from_arrays(rp, c, v, k)
+    B = rand_dense(n, k, 4)
+    gold = orc.spmm_ref(rp, c, v, B)
+    mat = fx.Mat(dl, fmt="tcw", tc_threshold=T, tc_width=W, tc_min_gain=min_gain)
+    o = assert_plan_equal(mat, rp, c, v, T=T, W=W, min_gain=min_gain)
+    if min_gain == 100000:
+        assert o["ntc"] == 0  # nothing qualifies: the whole matrix goes through the remainder
+    res = run_spmm(mat, B, n)
+    assert_close(orc, gold, res, rp)
+    mat.free()
+
+
+@pytest.mark.parametrize("name", ["a_mat.csv", "pubmed.csv"])
+def test_reference_matrices(orc, data_dir, name):
+    path = os.path.join(data_dir, name)
+    m = orc.csv_load(path)
+    rp, c, v = m["rowptr"], m["col"], m["val"]
+    n = rp.size - 1
+    k = 128
+    dl = fx.DataLoader(path, k)
+    B = orc.rand_B(n, k)
+    gold = orc.spmm_ref(rp, c, v, B)
+    mat = fx.Mat(dl, fmt="tcw", tc_threshold=2, tc_min_gain=8)
+    assert_plan_equal(mat, rp, c, v, T=2, min_gain=8)
+    res = run_spmm(mat, B, n)
+    assert_close(orc, gold, res, rp)
+    mat.free()
+
+
+def test_row_shards_and_rebuild(orc):
+    n, k = 2000, 128
+    rp, c, v = random_csr(n, 8, 11, hubs=1, blocks=10)
+    dl = fx.DataLoader.from_arrays(rp, c, v, k)
+    B = rand_dense(n, k, 9)
+    gold = orc.spmm_ref(rp, c, v, B)
+    parts = []
+    for lo, hi in ((0, 640), (640, 1408), (1408, n)):
+        mat = fx.Mat(dl, fmt="tcw", row_begin=lo, row_end=hi)
+        assert_plan_equal(mat, rp, c, v, row_begin=lo, row_end=hi)
+        mat.rebuild()
+        assert_plan_equal(mat, rp, c, v, row_begin=lo, row_end=hi)
+        parts.append(run_spmm(mat, B, hi - lo))
+        mat.free()
+    assert_close(orc, gold, np.concatenate(parts), rp)
+
+
+def test_dense_panel(orc):
+    """A fully dense 256 x 256 corner: every row of two panels shares every column."""
+    n, k = 640, 128
+    rng = np.random.default_rng(3)
+    A = np.zeros((n, n), np.float32)
+    A[:256, :256] = rng.random((256, 256)).astype(np.float32) * 2 - 1
+    A[np.arange(n), np.arange(n)] = 1.0
+    r, cidx = np.nonzero(A)
+    rp = np.zeros(n + 1, np.uint32); np.add.at(rp, r + 1, 1); rp = np.cumsum(rp).astype(np.uint32)
+    c = cidx.astype(np.uint32); v = A[r, cidx]
+    dl = fx.DataLoader.from_arrays(rp, c, v, k)
+    B = rand_dense(n, k, 1)
+    gold = orc.spmm_ref(rp, c, v, B)
+    mat = fx.Mat(dl, fmt="tcw")
+    o = assert_plan_equal(mat, rp, c, v)
+    assert o["tc_ncol"][0] == 256 and o["tc_ncol"][1] == 256
+    res = run_spmm(mat, B, n)
+    assert_close(orc, gold, res, rp)
+    mat.free()
