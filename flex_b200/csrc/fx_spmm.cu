@@ -591,11 +591,11 @@ static int launch_aspt(const fx_tiles* t, const PanelArgs& a, int special_p, cud
 
 template <int N>
 static int launch_tc(const fxtc::TcArgs& ta, int ntc, cudaStream_t s) {
-  const size_t smem = fxtc::tc_smem_bytes<N>();
-  static bool attr_set = false;
-  if (!attr_set) {
+  const size_t smem = fxtc::tc_smem_bytes<N>(ta.W);
+  static size_t attr_set = 0;
+  if (smem > attr_set) {
     FX_CUDA(cudaFuncSetAttribute(fxtc::k_spmm_tc<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set = smem;
   }
   dim3 grid(ntc, ceil_div(ta.k, N));
   fxtc::k_spmm_tc<N><<<grid, 256, smem, s>>>(ta);
@@ -617,6 +617,7 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
     ta.B = B; ta.out = w.tc_out; ta.k = k; ta.W = w.W;
     const int rc = KC == 32 ? launch_tc<32>(ta, w.ntc, s) : (KC == 64 ? launch_tc<64>(ta, w.ntc, s) : launch_tc<128>(ta, w.ntc, s));
     if (rc != FX_OK) return rc;
+    if (getenv("FLEX_TC_SYNC")) cudaStreamSynchronize(s);
     a.tc_out = w.tc_out; a.tc_slot = w.tc_slot;
   }
   a.mcsr_cnt = d.mcsr_cnt; a.mcsr_e = d.mcsr_e_use; a.mcsr_list = d.mcsr_list;

@@ -84,7 +84,7 @@ __device__ __forceinline__ uint32_t a_offset(int r, int kk, uint32_t SBO) {
   return (uint32_t)(r >> 3) * SBO + (uint32_t)(kk >> 2) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(kk & 3) * 4u;
 }
 
-// grid = (ntc, ceil(k / N)), block = 256.  Dynamic shared memory: 2*128*32*4 + 2*N*32*4 bytes, so three
+// grid = (ntc, ceil(k / N)), block = 256.  Dynamic shared memory: 2*128*32*4 + 2*N*32*4 + 4*W bytes, so three
 // CTAs share an SM and the staging of one overlaps the MMAs of another.
 template <int N>
 __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
   float* Alo = Ahi + TC_BH * TC_KCH;
   float* Bhi = Alo + TC_BH * TC_KCH;
   float* Blo = Bhi + TC_KCH * N;
+  int* scols = reinterpret_cast<int*>(Blo + TC_KCH * N);  // [W] the panel's column list
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < 2 * TC_BH * TC_KCH / 4; i += 256) reinterpret_cast<float4*>(Ahi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < a.W; i += 256) scols[i] = i < ncol ? __ldg(cols + i) : -1;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -121,29 +123,68 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
   const int nchunk = (ncol + TC_KCH - 1) / TC_KCH;
   const int* cptr = a.win_cptr + (size_t)panel * (a.W / TC_KCH);
 
-  for (int ch = 0; ch < nchunk; ++ch) {
+  // Software pipeline: the global loads of chunk ch+1 (B rows through the column list, the first
+  // nz of every thread) are issued into registers right after the MMAs of chunk ch, so their L2
+  // latency runs under the tensor pipe; conversion and the shared-memory stores follow the wait.
+  constexpr int IT = (TC_KCH / 4) * N / 256;  // B items (4 k of one feature) per thread: idx = tid + it*256
+  constexpr int NE = 4;                        // nz per thread kept in registers; longer chunks loop
+  static_assert(IT >= 1, "N too small for 256 threads");
+  float bx[IT][4];
+  uint32_t ecode[NE];
+  float eval[NE];
+  int eb = 0, ee = 0;
+  auto prefetch = [&](int ch) {
     const int s0 = ch * TC_KCH;
-    // stage, split and transpose the B rows of this chunk to K-major: a warp reads 128-byte runs of four
-    // B rows, each lane keeps one feature and stores its 4 k as one 16-byte word
-    for (int idx = tid; idx < (TC_KCH / 4) * N; idx += 256) {
-      const int n = idx % N, kq = idx / N;
-      float x[4];
+    eb = __ldg(cptr + ch); ee = __ldg(cptr + ch + 1);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int s = s0 + kq * 4 + j;
-        const int gcol = s < ncol ? __ldg(cols + s) : -1;
-        x[j] = (gcol >= 0 && n0 + n < a.k) ? __ldg(a.B + (size_t)gcol * a.k + n0 + n) : 0.f;
-      }
+    for (int it = 0; it < IT; ++it) {
+      const int idx = tid + it * 256, n = idx % N, kq = idx / N;
+      const int4 gc = *reinterpret_cast<const int4*>(scols + s0 + kq * 4);
+      const bool nok = n0 + n < a.k;
+      bx[it][0] = (gc.x >= 0 && nok) ? __ldg(a.B + (size_t)gc.x * a.k + n0 + n) : 0.f;
+      bx[it][1] = (gc.y >= 0 && nok) ? __ldg(a.B + (size_t)gc.y * a.k + n0 + n) : 0.f;
+      bx[it][2] = (gc.z >= 0 && nok) ? __ldg(a.B + (size_t)gc.z * a.k + n0 + n) : 0.f;
+      bx[it][3] = (gc.w >= 0 && nok) ? __ldg(a.B + (size_t)gc.w * a.k + n0 + n) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      const int e = eb + tid + q * 256;
+      ecode[q] = e < ee ? (uint32_t)a.win_code[e] : 0xFFFFFFFFu;
+      eval[q] = e < ee ? a.win_val[e] : 0.f;
+    }
+  };
+  if (nchunk > 0) prefetch(0);
+
+  for (int ch = 0; ch < nchunk; ++ch) {
+    // B rows of the chunk, split and transposed to K-major (a warp read 128-byte runs of four B
+    // rows; each lane keeps one feature and stores its 4 k as one 16-byte word)
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int idx = tid + it * 256, n = idx % N, kq = idx / N;
       float4 h, l;
-      h.x = to_tf32(x[0]); h.y = to_tf32(x[1]); h.z = to_tf32(x[2]); h.w = to_tf32(x[3]);
-      l.x = to_tf32(x[0] - h.x); l.y = to_tf32(x[1] - h.y); l.z = to_tf32(x[2] - h.z); l.w = to_tf32(x[3] - h.w);
+      h.x = to_tf32(bx[it][0]); h.y = to_tf32(bx[it][1]); h.z = to_tf32(bx[it][2]); h.w = to_tf32(bx[it][3]);
+      l.x = to_tf32(bx[it][0] - h.x); l.y = to_tf32(bx[it][1] - h.y); l.z = to_tf32(bx[it][2] - h.z); l.w = to_tf32(bx[it][3] - h.w);
       const uint32_t off = (uint32_t)(n >> 3) * SBO + (uint32_t)kq * LBO + (uint32_t)(n & 7) * 16u;
       *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(Bhi) + off) = h;
       *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(Blo) + off) = l;
     }
+    // every thread has cleared its words of the previous chunk before anyone writes the A tiles again
+    // (two chunks reuse the same (row, k) words)
+    if (ch > 0) __syncthreads();
     // scatter the chunk's nz into the (zeroed) A tiles, all threads at once
-    const int eb = __ldg(cptr + ch), ee = __ldg(cptr + ch + 1);
-    for (int e = eb + tid; e < ee; e += 256) {
+    uint32_t ccode[NE];
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+      ccode[q] = ecode[q];
+      if (ecode[q] != 0xFFFFFFFFu) {
+        const float h = to_tf32(eval[q]), l = to_tf32(eval[q] - h);
+        const uint32_t off = a_offset((int)(ecode[q] >> 5), (int)(ecode[q] & 31u), SBO);
+        *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Ahi) + off) = h;
+        *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Alo) + off) = l;
+      }
+    }
+    const int ceb = eb, cee = ee;
+    for (int e = ceb + tid + NE * 256; e < cee; e += 256) {
       const uint32_t code = a.win_code[e];
       const float v = a.win_val[e];
       const float h = to_tf32(v), l = to_tf32(v - h);
@@ -151,6 +192,7 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
       *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Ahi) + off) = h;
       *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Alo) + off) = l;
     }
+    if (ch + 1 < nchunk) prefetch(ch + 1);  // in flight under the barrier, the MMAs and their wait
     // generic-proxy writes -> visible to the tensor core's async proxy
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -172,7 +214,15 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // clear only the A words this chunk set
     if (ch + 1 < nchunk) {
-      for (int e = eb + tid; e < ee; e += 256) {
+#pragma unroll
+      for (int q = 0; q < NE; ++q) {
+        if (ccode[q] != 0xFFFFFFFFu) {
+          const uint32_t off = a_offset((int)(ccode[q] >> 5), (int)(ccode[q] & 31u), SBO);
+          *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Ahi) + off) = 0.f;
+          *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Alo) + off) = 0.f;
+        }
+      }
+      for (int e = ceb + tid + NE * 256; e < cee; e += 256) {
         const uint32_t code = a.win_code[e];
         const uint32_t off = a_offset((int)(code >> 5), (int)(code & 31u), SBO);
         *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Ahi) + off) = 0.f;
@@ -219,6 +269,6 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
 }
 
 template <int N>
-inline size_t tc_smem_bytes() { return (size_t)2 * TC_BH * TC_KCH * 4 + (size_t)2 * TC_KCH * N * 4; }
+inline size_t tc_smem_bytes(int W) { return (size_t)2 * TC_BH * TC_KCH * 4 + (size_t)2 * TC_KCH * N * 4 + (size_t)W * 4; }
 
 }  // namespace fxtc
