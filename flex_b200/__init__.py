@@ -45,7 +45,8 @@ class BuildOpts(C.Structure):
     _fields_ = [("format", C.c_int32), ("tm", C.c_int32), ("tn", C.c_int32), ("bw", C.c_int32),
                 ("nnz_limit", C.c_int32), ("n_sm", C.c_int32), ("row_begin", C.c_int32),
                 ("row_end", C.c_int32), ("cmajor", C.c_int32), ("tc_threshold", C.c_int32),
-                ("tc_width", C.c_int32), ("tc_min_gain", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("tc_width", C.c_int32), ("tc_min_gain", C.c_int32), ("tc_chunk_cost", C.c_int32),
+                ("tc_min_total", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class AsptArrays(C.Structure):
@@ -93,8 +94,9 @@ class PillarArrays(C.Structure):
 
 class TcwArrays(C.Structure):
     _fields_ = [("n", C.c_int32), ("nr", C.c_int32), ("npanel", C.c_int32), ("W", C.c_int32), ("T", C.c_int32),
-                ("min_gain", C.c_int32), ("ntc", C.c_int32), ("dropped", C.c_int32),
-                ("win_nnz", C.c_int64), ("rest_nnz", C.c_int64),
+                ("min_gain", C.c_int32), ("ntc", C.c_int32), ("dropped", C.c_int32), ("chunk_cost", C.c_int32),
+                ("reserved0", C.c_int32),
+                ("win_nnz", C.c_int64), ("rest_nnz", C.c_int64), ("min_total", C.c_int64), ("net_gain", C.c_int64),
                 ("tc_cols", C.POINTER(C.c_int32)), ("tc_ncol", C.POINTER(C.c_int32)),
                 ("win_cptr", C.POINTER(C.c_int32)), ("win_code", C.POINTER(C.c_uint16)),
                 ("win_val", C.POINTER(C.c_float)), ("rest_rowptr", C.POINTER(C.c_uint32)),
@@ -322,7 +324,7 @@ class Mat:
     ASpT: the pre-process section of process(), aspt/sspmm_128.cu:1207-1333)."""
 
     def __init__(self, dl, fmt="aspt", tm=4, tn=4, bw=0, row_begin=0, row_end=0, n_sm=0, cmajor=0, nnz_limit=0,
-                 tc_threshold=0, tc_width=0, tc_min_gain=0):
+                 tc_threshold=0, tc_width=0, tc_min_gain=0, tc_chunk_cost=0, tc_min_total=0):
         self.dl = dl
         self._h = C.c_void_p()
         o = BuildOpts()
@@ -330,6 +332,7 @@ class Mat:
         o.tm, o.tn, o.bw, o.n_sm, o.cmajor, o.nnz_limit = tm, tn, bw, n_sm, int(cmajor), nnz_limit
         o.row_begin, o.row_end = row_begin, row_end
         o.tc_threshold, o.tc_width, o.tc_min_gain = tc_threshold, tc_width, tc_min_gain
+        o.tc_chunk_cost, o.tc_min_total = tc_chunk_cost, tc_min_total
         self.fmt = o.format
         self.row_begin = row_begin
         self.row_end = row_end if (row_begin or row_end) else dl.n
@@ -404,6 +407,7 @@ class Mat:
         _ck(lib().fx_tiles_export_tcw(self._h, C.byref(a)))
         wn, rn = a.win_nnz, a.rest_nnz
         return dict(n=a.n, nr=a.nr, npanel=a.npanel, W=a.W, T=a.T, min_gain=a.min_gain, ntc=a.ntc, dropped=a.dropped,
+                    chunk_cost=a.chunk_cost, min_total=a.min_total, net_gain=a.net_gain,
                     win_nnz=wn, rest_nnz=rn,
                     tc_cols=_np(a.tc_cols, a.npanel * a.W, np.int32).copy().reshape(a.npanel, a.W),
                     tc_ncol=_np(a.tc_ncol, a.npanel, np.int32).copy(),

@@ -84,7 +84,9 @@ extern "C" int fx_build(const fx_matrix* m, const fx_build_opts* opts, fx_tiles*
       fx_tcw_dev& w = t->tcw;
       if (t->opts.tc_threshold) w.T = t->opts.tc_threshold;
       if (t->opts.tc_width) w.W = t->opts.tc_width;
-      if (t->opts.tc_min_gain) w.min_gain = t->opts.tc_min_gain;
+      if (t->opts.tc_min_gain) w.min_gain = std::max(0, t->opts.tc_min_gain);  // negative = no minimum
+      if (t->opts.tc_chunk_cost) w.chunk_cost = std::max(0, t->opts.tc_chunk_cost);
+      if (t->opts.tc_min_total) w.min_total = std::max(0, t->opts.tc_min_total);
       if (w.T < 2 || w.W < 32 || w.W > 4096 || w.W % 32) { fx::set_error("tc_threshold must be >= 2 and tc_width a multiple of 32 in [32,4096]"); return fail(FX_ERR_ARG); }
       extra = fx::tcw_arena_bytes(t);
     }

@@ -128,7 +128,8 @@ struct fx_aspt_dev {  // device-side ASpT format (aspt/sspmm_128.cu:76-90 global
 };
 
 struct fx_tcw_dev {  // tensor-window format (fx_tcw_build.cu): per-panel column lists + window nz + remainder CSR
-  int T = 4, W = 512, min_gain = 64;
+  int T = 4, W = 512, min_gain = 1024, chunk_cost = 224;
+  long long min_total = 1000000, net_gain = 0;
   int *tc_cols = nullptr, *tc_ncol = nullptr, *tc_slot = nullptr, *tc_panels = nullptr;
   int *csr_v = nullptr, *win_len = nullptr, *win_rowptr = nullptr, *chunk_len = nullptr, *win_cptr = nullptr;
   uint32_t *rest_rowptr = nullptr, *rest_col = nullptr;

@@ -617,7 +617,6 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
     ta.B = B; ta.out = w.tc_out; ta.k = k; ta.W = w.W;
     const int rc = KC == 32 ? launch_tc<32>(ta, w.ntc, s) : (KC == 64 ? launch_tc<64>(ta, w.ntc, s) : launch_tc<128>(ta, w.ntc, s));
     if (rc != FX_OK) return rc;
-    if (getenv("FLEX_TC_SYNC")) cudaStreamSynchronize(s);
     a.tc_out = w.tc_out; a.tc_slot = w.tc_slot;
   }
   a.mcsr_cnt = d.mcsr_cnt; a.mcsr_e = d.mcsr_e_use; a.mcsr_list = d.mcsr_list;

@@ -14,7 +14,8 @@
 // cute/atom/mma_traits_sm100.hpp:165-199), both operands K-major:
 //   A chunk [128 rows x 32 k] : core matrix = 8 rows x 16 B;  byte(r,kk) =
 //        (r/8)*SBO + (kk/4)*128 + (r%8)*16 + (kk%4)*4,  LBO = 128, SBO = 1024
-//   B chunk [N x 32 k] (B rows transposed while staging): the same formula with r = feature n.
+//   B chunk [N x 32 k] (B rows transposed while staging): the same formula with r = feature n (SBO = 1040
+//        in k_spmm_tc: see there).
 //        MN-major tf32 operands only work with the 128B_BASE32B swizzle on this part (probed with
 //        scripts/tc_probe.cu: every other layout type reads zeros), so B is transposed instead.
 // One K=8 step spans two K-adjacent core matrices of either operand (start += 256 B).
@@ -29,7 +30,7 @@ constexpr int TC_KCH = 32;  // window columns staged per step
 
 struct TcArgs {
   const int* win_cptr;       // [npanel*(W/32)+1] window nz of each (panel, 32-column chunk)
-  const uint16_t* win_code;  // (row in panel << 5) | (position in the chunk)
+  const uint16_t* win_code;  // word of the nz inside the chunk's 128 x 32 A tile (tile_word(row, k), below)
   const float* win_val;
   const int* tc_panels;      // [ntc] panels that have a window
   const int* tc_cols;        // [npanel][W] column list of each panel, -1 padded
@@ -80,8 +81,10 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity)
       "TC_DONE:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
 
-__device__ __forceinline__ uint32_t a_offset(int r, int kk, uint32_t SBO) {
-  return (uint32_t)(r >> 3) * SBO + (uint32_t)(kk >> 2) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(kk & 3) * 4u;
+// 4-byte word of element (r, kk) in a K-major 128 x 32 tile with LBO = 128, SBO = 1024 bytes: the builder
+// stores this number per window nz, so the scatter is one shift and two stores
+__host__ __device__ __forceinline__ uint32_t tile_word(int r, int kk) {
+  return ((uint32_t)(r >> 3) << 8) | ((uint32_t)(kk >> 2) << 5) | ((uint32_t)(r & 7) << 2) | (uint32_t)(kk & 3);
 }
 
 // grid = (ntc, ceil(k / N)), block = 256.  Dynamic shared memory: 2*128*32*4 + 2*N*32*4 + 4*W bytes, so three
@@ -90,12 +93,16 @@ template <int N>
 __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
   constexpr int TM_COLS = N < 32 ? 32 : N;
   constexpr uint32_t LBO = 128, SBO = (TC_KCH / 4) * 128;
+  // B tiles: 16 extra bytes between 8-feature groups, so that the 16-byte stores of a warp whose lanes hold
+  // four consecutive features each (two lanes per group) fall on all 32 banks
+  constexpr uint32_t SBO_B = SBO + 16, B_BYTES = (N / 8) * SBO_B;
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   float* Ahi = reinterpret_cast<float*>(tc_smem);
   float* Alo = Ahi + TC_BH * TC_KCH;
-  float* Bhi = Alo + TC_BH * TC_KCH;
-  float* Blo = Bhi + TC_KCH * N;
-  int* scols = reinterpret_cast<int*>(Blo + TC_KCH * N);  // [W] the panel's column list
+  unsigned char* Bhi = reinterpret_cast<unsigned char*>(Alo + TC_BH * TC_KCH);
+  unsigned char* Blo = Bhi + B_BYTES;
+  int* scols = reinterpret_cast<int*>(Blo + B_BYTES);  // [W] the panel's column list
+  int* scptr = scols + a.W;                            // [W/32 + 1] nz range of every chunk
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -113,6 +120,7 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
   }
   for (int i = tid; i < 2 * TC_BH * TC_KCH / 4; i += 256) reinterpret_cast<float4*>(Ahi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = tid; i < a.W; i += 256) scols[i] = i < ncol ? __ldg(cols + i) : -1;
+  for (int i = tid; i <= a.W / TC_KCH; i += 256) scptr[i] = __ldg(a.win_cptr + (size_t)panel * (a.W / TC_KCH) + i);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -121,30 +129,34 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
 
   uint32_t phase = 0;
   const int nchunk = (ncol + TC_KCH - 1) / TC_KCH;
-  const int* cptr = a.win_cptr + (size_t)panel * (a.W / TC_KCH);
 
-  // Software pipeline: the global loads of chunk ch+1 (B rows through the column list, the first
-  // nz of every thread) are issued into registers right after the MMAs of chunk ch, so their L2
-  // latency runs under the tensor pipe; conversion and the shared-memory stores follow the wait.
-  constexpr int IT = (TC_KCH / 4) * N / 256;  // B items (4 k of one feature) per thread: idx = tid + it*256
-  constexpr int NE = 4;                        // nz per thread kept in registers; longer chunks loop
-  static_assert(IT >= 1, "N too small for 256 threads");
-  float bx[IT][4];
+  // Software pipeline: the global loads of chunk ch+1 (B rows through the column list, the first nz
+  // of every thread) are issued into registers before the MMAs of chunk ch, so their L2 latency runs
+  // under the barrier, the tensor pipe and its wait; conversion and the shared-memory stores follow.
+  // A thread owns one 4 x 4 unit of the chunk: B rows kq*4..+3, features fq*4..+3 (one 16-byte load per
+  // row, a warp reads whole 512-byte rows), transposed in registers into four 16-byte words of 4 k.
+  constexpr int UNITS = 2 * N;  // (32 / 4) * (N / 4)
+  constexpr int NE = 4;         // nz per thread kept in registers; longer chunks loop
+  const int fq = tid % (N / 4), kq = tid / (N / 4);
+  const bool unit_ok = tid < UNITS && n0 + fq * 4 < a.k;
+  const float4* Bq = reinterpret_cast<const float4*>(a.B + n0 + fq * 4);
+  const size_t k4 = (size_t)a.k / 4;
+  float4 bx[4];
   uint32_t ecode[NE];
   float eval[NE];
   int eb = 0, ee = 0;
   auto prefetch = [&](int ch) {
-    const int s0 = ch * TC_KCH;
-    eb = __ldg(cptr + ch); ee = __ldg(cptr + ch + 1);
-#pragma unroll
-    for (int it = 0; it < IT; ++it) {
-      const int idx = tid + it * 256, n = idx % N, kq = idx / N;
-      const int4 gc = *reinterpret_cast<const int4*>(scols + s0 + kq * 4);
-      const bool nok = n0 + n < a.k;
-      bx[it][0] = (gc.x >= 0 && nok) ? __ldg(a.B + (size_t)gc.x * a.k + n0 + n) : 0.f;
-      bx[it][1] = (gc.y >= 0 && nok) ? __ldg(a.B + (size_t)gc.y * a.k + n0 + n) : 0.f;
-      bx[it][2] = (gc.z >= 0 && nok) ? __ldg(a.B + (size_t)gc.z * a.k + n0 + n) : 0.f;
-      bx[it][3] = (gc.w >= 0 && nok) ? __ldg(a.B + (size_t)gc.w * a.k + n0 + n) : 0.f;
+    eb = scptr[ch]; ee = scptr[ch + 1];
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    bx[0] = z; bx[1] = z; bx[2] = z; bx[3] = z;
+    if (tid < UNITS) {
+      const int4 gc = *reinterpret_cast<const int4*>(scols + ch * TC_KCH + kq * 4);
+      if (unit_ok) {
+        if (gc.x >= 0) bx[0] = __ldg(Bq + (size_t)gc.x * k4);
+        if (gc.y >= 0) bx[1] = __ldg(Bq + (size_t)gc.y * k4);
+        if (gc.z >= 0) bx[2] = __ldg(Bq + (size_t)gc.z * k4);
+        if (gc.w >= 0) bx[3] = __ldg(Bq + (size_t)gc.w * k4);
+      }
     }
 #pragma unroll
     for (int q = 0; q < NE; ++q) {
@@ -156,17 +168,19 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
   if (nchunk > 0) prefetch(0);
 
   for (int ch = 0; ch < nchunk; ++ch) {
-    // B rows of the chunk, split and transposed to K-major (a warp read 128-byte runs of four B
-    // rows; each lane keeps one feature and stores its 4 k as one 16-byte word)
+    if (tid < UNITS) {
+      const float xs[4][4] = {{bx[0].x, bx[1].x, bx[2].x, bx[3].x}, {bx[0].y, bx[1].y, bx[2].y, bx[3].y},
+                              {bx[0].z, bx[1].z, bx[2].z, bx[3].z}, {bx[0].w, bx[1].w, bx[2].w, bx[3].w}};
 #pragma unroll
-    for (int it = 0; it < IT; ++it) {
-      const int idx = tid + it * 256, n = idx % N, kq = idx / N;
-      float4 h, l;
-      h.x = to_tf32(bx[it][0]); h.y = to_tf32(bx[it][1]); h.z = to_tf32(bx[it][2]); h.w = to_tf32(bx[it][3]);
-      l.x = to_tf32(bx[it][0] - h.x); l.y = to_tf32(bx[it][1] - h.y); l.z = to_tf32(bx[it][2] - h.z); l.w = to_tf32(bx[it][3] - h.w);
-      const uint32_t off = (uint32_t)(n >> 3) * SBO + (uint32_t)kq * LBO + (uint32_t)(n & 7) * 16u;
-      *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(Bhi) + off) = h;
-      *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(Blo) + off) = l;
+      for (int i = 0; i < 4; ++i) {
+        const int n = fq * 4 + i;
+        float4 h, l;
+        h.x = to_tf32(xs[i][0]); h.y = to_tf32(xs[i][1]); h.z = to_tf32(xs[i][2]); h.w = to_tf32(xs[i][3]);
+        l.x = to_tf32(xs[i][0] - h.x); l.y = to_tf32(xs[i][1] - h.y); l.z = to_tf32(xs[i][2] - h.z); l.w = to_tf32(xs[i][3] - h.w);
+        const uint32_t off = (uint32_t)(n >> 3) * SBO_B + (uint32_t)kq * LBO + (uint32_t)(n & 7) * 16u;
+        *reinterpret_cast<float4*>(Bhi + off) = h;
+        *reinterpret_cast<float4*>(Blo + off) = l;
+      }
     }
     // every thread has cleared its words of the previous chunk before anyone writes the A tiles again
     // (two chunks reuse the same (row, k) words)
@@ -178,9 +192,8 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
       ccode[q] = ecode[q];
       if (ecode[q] != 0xFFFFFFFFu) {
         const float h = to_tf32(eval[q]), l = to_tf32(eval[q] - h);
-        const uint32_t off = a_offset((int)(ecode[q] >> 5), (int)(ecode[q] & 31u), SBO);
-        *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Ahi) + off) = h;
-        *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Alo) + off) = l;
+        Ahi[ecode[q]] = h;
+        Alo[ecode[q]] = l;
       }
     }
     const int ceb = eb, cee = ee;
@@ -188,13 +201,14 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
       const uint32_t code = a.win_code[e];
       const float v = a.win_val[e];
       const float h = to_tf32(v), l = to_tf32(v - h);
-      const uint32_t off = a_offset((int)(code >> 5), (int)(code & 31u), SBO);
-      *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Ahi) + off) = h;
-      *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Alo) + off) = l;
+      Ahi[code] = h;
+      Alo[code] = l;
     }
-    if (ch + 1 < nchunk) prefetch(ch + 1);  // in flight under the barrier, the MMAs and their wait
-    // generic-proxy writes -> visible to the tensor core's async proxy
+    // generic-proxy writes -> visible to the tensor core's async proxy.  The fence is a full membar: it waits
+    // for every outstanding load of the thread, so the prefetch is issued AFTER it and stays in flight under
+    // the barrier, the MMAs and their wait
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (ch + 1 < nchunk) prefetch(ch + 1);
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -202,7 +216,7 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
 #pragma unroll
       for (int ks = 0; ks < TC_KCH / 8; ++ks) {
         const uint64_t dah = make_desc(ahi + ks * 2 * LBO, LBO, SBO), dal = make_desc(alo + ks * 2 * LBO, LBO, SBO);
-        const uint64_t dbh = make_desc(bhi + ks * 2 * LBO, LBO, SBO), dbl = make_desc(blo + ks * 2 * LBO, LBO, SBO);
+        const uint64_t dbh = make_desc(bhi + ks * 2 * LBO, LBO, SBO_B), dbl = make_desc(blo + ks * 2 * LBO, LBO, SBO_B);
         mma_tf32(tmem, dah, dbh, idesc, (ch | ks) ? 1u : 0u);
         mma_tf32(tmem, dah, dbl, idesc, 1u);
         mma_tf32(tmem, dal, dbh, idesc, 1u);
@@ -216,17 +230,12 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
     if (ch + 1 < nchunk) {
 #pragma unroll
       for (int q = 0; q < NE; ++q) {
-        if (ccode[q] != 0xFFFFFFFFu) {
-          const uint32_t off = a_offset((int)(ccode[q] >> 5), (int)(ccode[q] & 31u), SBO);
-          *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Ahi) + off) = 0.f;
-          *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Alo) + off) = 0.f;
-        }
+        if (ccode[q] != 0xFFFFFFFFu) { Ahi[ccode[q]] = 0.f; Alo[ccode[q]] = 0.f; }
       }
       for (int e = ceb + tid + NE * 256; e < cee; e += 256) {
         const uint32_t code = a.win_code[e];
-        const uint32_t off = a_offset((int)(code >> 5), (int)(code & 31u), SBO);
-        *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Ahi) + off) = 0.f;
-        *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Alo) + off) = 0.f;
+        Ahi[code] = 0.f;
+        Alo[code] = 0.f;
       }
     }
   }
@@ -269,6 +278,8 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
 }
 
 template <int N>
-inline size_t tc_smem_bytes(int W) { return (size_t)2 * TC_BH * TC_KCH * 4 + (size_t)2 * TC_KCH * N * 4 + (size_t)W * 4; }
+inline size_t tc_smem_bytes(int W) {
+  return (size_t)2 * TC_BH * TC_KCH * 4 + (size_t)2 * (N / 8) * ((TC_KCH / 4) * 128 + 16) + (size_t)W * 4 + (size_t)(W / TC_KCH + 1) * 4;
+}
 
 }  // namespace fxtc

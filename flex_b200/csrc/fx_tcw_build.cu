@@ -6,7 +6,7 @@
 //   per 128-row panel p : S_p = the (at most W) columns with the most nz in the panel, each with
 //                         at least T of them, ascending                      -> tc_cols / tc_ncol
 //   window part         : the nz whose column is in S_p, grouped by (panel, 32-column chunk of S_p) and
-//                         ordered by (row, slot) inside a chunk, as (row-in-panel<<5 | slot&31, value):
+//                         ordered by (row, slot) inside a chunk, as (word of (row, slot&31) in the K-major A tile, value):
 //                         one chunk is one K=32 step of the tensor kernel, which scatters its entries with
 //                         all threads at once                                -> win_cptr/code/val
 //   remainder           : every other nz as an ordinary CSR                  -> rest_rowptr/col/val
@@ -14,16 +14,23 @@
 // multiplied by k_spmm_tc (fx_tc_kernel.cuh).  oracle/fx_oracle_tcw.c restates the selection rule
 // on the CPU; tests compare every array bit for bit.
 //
-// Selection rule (deterministic):  cnt_p[c] = nz of panel p in column c;  candidates = {c : cnt >= T'}
-// where T' = T, doubled until at most CAND_CAP candidates remain (at most 6 doublings, else the
-// panel gets no window);  order candidates by (cnt descending, column ascending), keep the first
-// min(W, #candidates);  the panel keeps its window only if  sum(cnt) - #kept >= MIN_GAIN  (B-row
-// fetches saved).  Kept columns are listed ascending.
+// Selection rule (deterministic, all integer):  cnt_p[c] = nz of panel p in column c;  candidates =
+// {c : cnt >= T'} where T' = T, doubled until at most CAND_CAP candidates remain (at most 6 doublings,
+// else the panel gets no window);  order candidates by (cnt descending, column ascending) and cut them
+// into chunks of 32 (one K=32 step of the tensor kernel), at most W/32 of them;  S_j = sum over chunk j
+// of (cnt - 1) is the number of B-row fetches the chunk saves the gather path;  keep the leading chunks
+// with S_j >= CHUNK_COST (what staging + 12 MMAs cost, in the same unit);  the panel keeps its window
+// only if  G_p = sum(S_j - CHUNK_COST) >= MIN_GAIN  (the tc_out round trip of the panel);  the whole
+// matrix keeps its windows only if  sum_p G_p >= MIN_TOTAL  (an extra kernel launch and its tail).
+// Kept columns are listed ascending.  Costs measured on a B200 at k = 128: DESIGN.md section 5.
 #include <cooperative_groups.h>
 #include <cooperative_groups/reduce.h>
 #include <cooperative_groups/scan.h>
 
+#include <algorithm>
+
 #include "fx_common.cuh"
+#include "fx_tc_kernel.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -65,22 +72,24 @@ __global__ void k_tcw_pad(const uint32_t* __restrict__ rowptr, int row0, int nlo
   if (i <= nr) csr_v[i] = i <= nloc ? (int)(rowptr[row0 + i] - rowptr[row0]) : ne;
 }
 
-// stats: [0] window nz, [1] listed columns, [2] panels with a window, [3] panels dropped by the cap
+// stats: [3] panels dropped by the candidate cap, [5] total net gain (the rest is filled by k_tcw_panels)
 __global__ void __launch_bounds__(512) k_tcw_select(const int* __restrict__ csr_v, const uint32_t* __restrict__ col, int npanel,
-                                                    int ncols, int T, int W, int min_gain, unsigned* __restrict__ cnt_all,
+                                                    int ncols, int T, int W, int min_gain, int chunk_cost,
+                                                    unsigned* __restrict__ cnt_all,
                                                     int* __restrict__ tc_cols, int* __restrict__ tc_ncol,
                                                     int* __restrict__ win_len, int* __restrict__ chunk_len,
                                                     unsigned long long* __restrict__ stats) {
   extern __shared__ unsigned long long skeys[];  // CAND_CAP
   __shared__ int s_nc;
   __shared__ int hist[MAX_CH];
+  __shared__ int s_ns;
+  __shared__ long long s_gain;
   const int CH = W / 32;
-  __shared__ long long s_sum;
   unsigned* cnt = cnt_all + (size_t)blockIdx.x * ncols;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   for (int p = blockIdx.x; p < npanel; p += gridDim.x) {
     const int lb = csr_v[p * BH], ub = csr_v[(p + 1) * BH];
-    if (threadIdx.x == 0) { s_nc = 0; s_sum = 0; }
+    if (threadIdx.x == 0) s_nc = 0;
     __syncthreads();
     // pass 1: count; the T-th hit of a column registers it
     for (int e = lb + threadIdx.x; e < ub; e += blockDim.x) {
@@ -121,25 +130,32 @@ __global__ void __launch_bounds__(512) k_tcw_select(const int* __restrict__ csr_
       }
       __syncthreads();
       tcw_sort_u64(skeys, nc);
-      ns = nc < W ? nc : W;
-      long long part = 0;
-      for (int i = threadIdx.x; i < ns; i += blockDim.x) part += (long long)(0xFFFFFFFFu - (unsigned)(skeys[i] >> 32));
-      part = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), part, cg::plus<long long>());
-      if (lane == 0 && part) atomicAdd((unsigned long long*)&s_sum, (unsigned long long)part);
+      const int m = nc < W ? nc : W, mch = (m + 31) / 32;
+      // S_j per chunk of 32 candidates (one warp per chunk), then the leading chunks that pay
+      for (int j = warp; j < mch; j += nwarp) {
+        const int i = j * 32 + lane;
+        int sj = i < m ? (int)(0xFFFFFFFFu - (unsigned)(skeys[i] >> 32)) - 1 : 0;
+        sj = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), sj, cg::plus<int>());
+        if (lane == 0) hist[j] = sj;
+      }
       __syncthreads();
-      const long long captured = s_sum;
-      if (captured - ns < min_gain) ns = 0;
+      if (threadIdx.x == 0) {
+        int j = 0;
+        long long g = 0;
+        while (j < mch && hist[j] >= chunk_cost) { g += hist[j] - chunk_cost; ++j; }
+        s_ns = g >= min_gain ? min(m, 32 * j) : 0;
+        s_gain = g >= min_gain ? g : 0;
+      }
+      __syncthreads();
+      ns = s_ns;
+      const long long captured = s_gain;
       __syncthreads();
       if (ns > 0) {
         for (int i = threadIdx.x; i < ns; i += blockDim.x) skeys[i] &= 0xFFFFFFFFull;  // keep the column only
         __syncthreads();
         tcw_sort_u64(skeys, ns);
         for (int i = threadIdx.x; i < ns; i += blockDim.x) cnt[(unsigned)skeys[i]] = MARK | (unsigned)i;
-        if (threadIdx.x == 0) {
-          atomicAdd(&stats[0], (unsigned long long)captured);
-          atomicAdd(&stats[1], (unsigned long long)ns);
-          atomicAdd(&stats[2], 1ull);
-        }
+        if (threadIdx.x == 0) atomicAdd(&stats[5], (unsigned long long)captured);  // total net gain
       }
     } else if (nc > CAND_CAP && threadIdx.x == 0) {
       atomicAdd(&stats[3], 1ull);
@@ -167,6 +183,18 @@ __global__ void __launch_bounds__(512) k_tcw_select(const int* __restrict__ csr_
     for (int e = lb + threadIdx.x; e < ub; e += blockDim.x) cnt[col[e]] = 0u;
     __syncthreads();
   }
+}
+
+// MIN_TOTAL gate: windows that together do not pay for a second kernel are dropped, on the device
+__global__ void k_tcw_gate(const unsigned long long* __restrict__ stats, long long min_total, int npanel, int nr, int W,
+                           int* __restrict__ tc_cols, int* __restrict__ tc_ncol, int* __restrict__ win_len,
+                           int* __restrict__ chunk_len) {
+  if ((long long)stats[5] >= min_total) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (long long)npanel * W) tc_cols[i] = -1;
+  if (i < npanel) tc_ncol[i] = 0;
+  if (i < nr) win_len[i] = 0;
+  if (i < (long long)npanel * (W / 32)) chunk_len[i] = 0;
 }
 
 // exclusive scan by one CTA: out[n] = total
@@ -204,8 +232,9 @@ __global__ void k_tcw_rowptr(const int* __restrict__ csr_v, const int* __restric
 }
 
 // ascending list of the panels that have a window; tc_slot[p] = position in that list or -1
-__global__ void __launch_bounds__(1024) k_tcw_panels(const int* __restrict__ tc_ncol, int npanel, int* __restrict__ tc_panels,
-                                                     int* __restrict__ tc_slot, int* __restrict__ ntc) {
+__global__ void __launch_bounds__(1024) k_tcw_panels(const int* __restrict__ tc_ncol, const int* __restrict__ win_rowptr, int npanel,
+                                                     int nr, int* __restrict__ tc_panels, int* __restrict__ tc_slot,
+                                                     unsigned long long* __restrict__ stats) {
   __shared__ int warp_sum[32];
   __shared__ int carry_s;
   auto warp = cg::tiled_partition<32>(cg::this_thread_block());
@@ -232,7 +261,12 @@ __global__ void __launch_bounds__(1024) k_tcw_panels(const int* __restrict__ tc_
     if (threadIdx.x == blockDim.x - 1) carry_s = incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *ntc = carry_s;
+  // stats: [0] window nz, [1] listed columns, [2] panels with a window
+  long long cols = 0;
+  for (int i = threadIdx.x; i < npanel; i += blockDim.x) cols += tc_ncol[i];
+  cols = cg::reduce(warp, cols, cg::plus<long long>());
+  if ((threadIdx.x & 31) == 0 && cols) atomicAdd(&stats[1], (unsigned long long)cols);
+  if (threadIdx.x == 0) { stats[2] = (unsigned long long)carry_s; stats[0] = (unsigned long long)win_rowptr[nr]; }
 }
 
 // split of every row into its window part (chunk-major inside the panel) and its remainder (row order)
@@ -305,7 +339,7 @@ __global__ void __launch_bounds__(512) k_tcw_split(const int* __restrict__ csr_v
           pc = __popc(peers);
           const int rank = __popc(peers & lt) + (ch == last_ch ? last_cnt : 0);
           const int pos = wbase + off2[ch * BH + r] + rank;
-          win_code[pos] = (uint16_t)((r << 5) | (s & 31));
+          win_code[pos] = (uint16_t)fxtc::tile_word(r, s & 31);
           win_val[pos] = v;
         } else if (valid) {
           const int pos = ro + __popc(mr & lt);
@@ -392,15 +426,21 @@ int tcw_build(fx_tiles* t, cudaStream_t s) {
     attr_set = true;
   }
   k_tcw_select<<<a.G, 512, CAND_CAP * sizeof(unsigned long long), s>>>(w.csr_v, col, a.npanel, (int)m->n, w.T, w.W, w.min_gain,
-                                                                      a.cnt_scratch, w.tc_cols, w.tc_ncol, w.win_len, w.chunk_len, w.stats);
+                                                                      w.chunk_cost, a.cnt_scratch, w.tc_cols, w.tc_ncol, w.win_len, w.chunk_len, w.stats);
   FX_LAUNCH_CHECK();
+  {
+    const long long cells = std::max<long long>((long long)a.npanel * w.W, a.nr);
+    k_tcw_gate<<<ceil_div(cells, 256), 256, 0, s>>>(w.stats, w.min_total, a.npanel, a.nr, w.W, w.tc_cols, w.tc_ncol, w.win_len,
+                                                     w.chunk_len);
+    FX_LAUNCH_CHECK();
+  }
   k_tcw_scan<<<1, 1024, 0, s>>>(w.win_len, a.nr, w.win_rowptr);
   FX_LAUNCH_CHECK();
   k_tcw_scan<<<1, 1024, 0, s>>>(w.chunk_len, a.npanel * (w.W / 32), w.win_cptr);
   FX_LAUNCH_CHECK();
   k_tcw_rowptr<<<ceil_div(nloc + 1, 256), 256, 0, s>>>(w.csr_v, w.win_rowptr, nloc, w.rest_rowptr);
   FX_LAUNCH_CHECK();
-  k_tcw_panels<<<1, 1024, 0, s>>>(w.tc_ncol, a.npanel, w.tc_panels, w.tc_slot, reinterpret_cast<int*>(w.stats + 4));
+  k_tcw_panels<<<1, 1024, 0, s>>>(w.tc_ncol, w.win_rowptr, a.npanel, a.nr, w.tc_panels, w.tc_slot, w.stats);
   FX_LAUNCH_CHECK();
   const size_t split_smem = sizeof(int) * (size_t)(w.W / 32) * BH;
   static size_t split_set = 0;
@@ -417,6 +457,7 @@ int tcw_build(fx_tiles* t, cudaStream_t s) {
   w.ncols_listed = (long long)t->stats_host[1];
   w.ntc = (int)t->stats_host[2];
   w.dropped = (int)t->stats_host[3];
+  w.net_gain = (long long)t->stats_host[5];
   // the remainder is what the ASpT builder sees
   t->src_rowptr = w.rest_rowptr;
   t->src_row0 = 0;
@@ -452,7 +493,7 @@ extern "C" int fx_tiles_export_tcw(fx_tiles* t, fx_tcw_arrays* o) {
   if ((rc = tcw_d2h(w.h_rest_col, w.rest_col, rest))) return rc;
   if ((rc = tcw_d2h(w.h_rest_val, w.rest_val, rest))) return rc;
   o->n = nloc; o->nr = a.nr; o->npanel = a.npanel; o->W = w.W; o->T = w.T; o->min_gain = w.min_gain;
-  o->ntc = w.ntc; o->dropped = w.dropped;
+  o->ntc = w.ntc; o->dropped = w.dropped; o->chunk_cost = w.chunk_cost; o->min_total = w.min_total; o->net_gain = w.net_gain;
   o->win_nnz = w.win_nnz; o->rest_nnz = (int64_t)rest;
   o->tc_cols = w.h_cols.data(); o->tc_ncol = w.h_ncol.data(); o->win_cptr = w.h_win_cptr.data();
   o->win_code = w.h_win_code.data(); o->win_val = w.h_win_val.data();

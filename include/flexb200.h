@@ -69,10 +69,13 @@ typedef struct {
   int32_t n_sm;       /* SM count for F4/F5 bucketing, 0 = device value */
   int32_t row_begin, row_end; /* build only rows [row_begin,row_end) (row-panel shard); 0,0 = all */
   int32_t cmajor;     /* FX_FMT_TILE: 0 = csr2flex_Rmajor, 1 = csr2flex_Cmajor (COL_MAJ_TILE, DataLoader.cuh:18) */
-  int32_t tc_threshold; /* FX_FMT_TCW: a column joins a panel's tensor window with >= this many nz in the panel (0 = 4) */
-  int32_t tc_width;     /* FX_FMT_TCW: at most this many window columns per panel (0 = 512) */
-  int32_t tc_min_gain;  /* FX_FMT_TCW: a panel keeps its window only if it saves >= this many B-row fetches (0 = 64) */
-  int32_t reserved[4];
+  /* FX_FMT_TCW plan (flex_b200/csrc/fx_tcw_build.cu has the rule); 0 = default; negative tc_min_* = "no minimum" */
+  int32_t tc_threshold;  /* a column is a candidate with >= this many nz in the panel (4) */
+  int32_t tc_width;      /* at most this many window columns per panel, multiple of 32 (512) */
+  int32_t tc_min_gain;   /* a panel keeps its window only if its net gain, in B-row fetches, reaches this (1024) */
+  int32_t tc_chunk_cost; /* what one 32-column chunk costs, in B-row fetches (224) */
+  int32_t tc_min_total;  /* the matrix keeps its windows only if the summed net gain reaches this (1000000) */
+  int32_t reserved[2];
 } fx_build_opts;
 
 typedef struct { /* ASpT metadata export for bit-exact checks; pointers are host copies
@@ -114,12 +117,13 @@ typedef struct { /* diagonal tiling / pillar format (mat.cu:680-903; Mat_POD mat
 } fx_pillar_arrays;
 
 typedef struct { /* tensor-window format (FX_FMT_TCW), host copies owned by the handle */
-  int32_t n, nr, npanel, W, T, min_gain, ntc, dropped;
-  int64_t win_nnz, rest_nnz;
+  int32_t n, nr, npanel, W, T, min_gain, ntc, dropped, chunk_cost, reserved0;
+  int64_t win_nnz, rest_nnz, min_total, net_gain;
   const int32_t *tc_cols;     /* npanel*W : ascending column list of each panel, -1 padded (W a multiple of 32) */
   const int32_t *tc_ncol;     /* npanel */
   const int32_t *win_cptr;    /* npanel*(W/32)+1 : window nz of each (panel, 32-column chunk of its list) */
-  const uint16_t *win_code;   /* win_nnz : (row in panel << 5) | (list position & 31), (row, position) order in a chunk */
+  const uint16_t *win_code;   /* win_nnz : word of (row r in panel, kk = list position & 31) in the chunk's K-major 128x32 operand
+                                 tile: (r>>3)<<8 | (kk>>2)<<5 | (r&7)<<2 | (kk&3); (row, position) order in a chunk */
   const float *win_val;       /* win_nnz */
   const uint32_t *rest_rowptr; /* n+1 */
   const uint32_t *rest_col;    /* rest_nnz */

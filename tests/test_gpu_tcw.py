@@ -22,7 +22,7 @@ ARRAYS = ("tc_cols", "tc_ncol", "win_cptr", "win_code", "win_val", "rest_rowptr"
 def assert_plan_equal(mat, rp, c, v, **kw):
     e = mat.export_tcw()
     o = tcw_oracle.plan(rp, c, v, **kw)
-    for f in ("n", "nr", "npanel", "W", "T", "ntc", "win_nnz", "rest_nnz"):
+    for f in ("n", "nr", "npanel", "W", "T", "ntc", "win_nnz", "rest_nnz", "net_gain"):
         assert e[f] == o[f], (f, e[f], o[f])
     for f in ARRAYS:
         assert np.array_equal(e[f], o[f]), f
@@ -36,8 +36,8 @@ def test_planted_blocks(orc, k):
     dl = fx.DataLoader.from_arrays(rp, c, v, k)
     B = rand_dense(n, k, 3)
     gold = orc.spmm_ref(rp, c, v, B)
-    mat = fx.Mat(dl, fmt="tcw")
-    o = assert_plan_equal(mat, rp, c, v)
+    mat = fx.Mat(dl, fmt="tcw", tc_min_total=-1)
+    o = assert_plan_equal(mat, rp, c, v, min_total=0)
     assert o["ntc"] > 0 and o["win_nnz"] > 0
     rp2, c2, v2 = tcw_oracle.reassemble(o)
     assert np.array_equal(rp2, rp.astype(np.int64)) and np.array_equal(c2, c.astype(np.int64)) and np.array_equal(v2, v)
@@ -46,16 +46,20 @@ def test_planted_blocks(orc, k):
     mat.free()
 
 
-@pytest.mark.parametrize("T,W,min_gain", [(2, 64, 1), (3, 32, 16), (8, 1024, 64), (4, 512, 100000)])
-def test_plan_parameters(orc, T, W, min_gain):
+@pytest.mark.parametrize("T,W,min_gain,chunk_cost,min_total", [
+    (2, 64, 1, 8, -1), (3, 32, 16, 40, -1), (8, 1024, 64, 224, -1), (4, 512, 100000, 224, -1), (4, 512, -1, -1, -1),
+    (4, 512, 64, 100, 30000), (4, 512, 64, 100, 10**9)])
+def test_plan_parameters(orc, T, W, min_gain, chunk_cost, min_total):
     n, k = 1100, 64
     rp, c, v = random_csr(n, 9, 5, hubs=1, blocks=6)
     dl = fx.DataLoader.from_arrays(rp, c, v, k)
     B = rand_dense(n, k, 4)
     gold = orc.spmm_ref(rp, c, v, B)
-    mat = fx.Mat(dl, fmt="tcw", tc_threshold=T, tc_width=W, tc_min_gain=min_gain)
-    o = assert_plan_equal(mat, rp, c, v, T=T, W=W, min_gain=min_gain)
-    if min_gain == 100000:
+    mat = fx.Mat(dl, fmt="tcw", tc_threshold=T, tc_width=W, tc_min_gain=min_gain, tc_chunk_cost=chunk_cost,
+                 tc_min_total=min_total)
+    o = assert_plan_equal(mat, rp, c, v, T=T, W=W, min_gain=max(0, min_gain), chunk_cost=max(0, chunk_cost),
+                          min_total=max(0, min_total))
+    if min_gain == 100000 or min_total == 10**9:
         assert o["ntc"] == 0  # nothing qualifies: the whole matrix goes through the remainder
     res = run_spmm(mat, B, n)
     assert_close(orc, gold, res, rp)
@@ -72,8 +76,8 @@ def test_reference_matrices(orc, data_dir, name):
     dl = fx.DataLoader(path, k)
     B = orc.rand_B(n, k)
     gold = orc.spmm_ref(rp, c, v, B)
-    mat = fx.Mat(dl, fmt="tcw", tc_threshold=2, tc_min_gain=8)
-    assert_plan_equal(mat, rp, c, v, T=2, min_gain=8)
+    mat = fx.Mat(dl, fmt="tcw", tc_threshold=2, tc_min_gain=8, tc_chunk_cost=16, tc_min_total=-1)
+    assert_plan_equal(mat, rp, c, v, T=2, min_gain=8, chunk_cost=16, min_total=0)
     res = run_spmm(mat, B, n)
     assert_close(orc, gold, res, rp)
     mat.free()
@@ -87,10 +91,10 @@ def test_row_shards_and_rebuild(orc):
     gold = orc.spmm_ref(rp, c, v, B)
     parts = []
     for lo, hi in ((0, 640), (640, 1408), (1408, n)):
-        mat = fx.Mat(dl, fmt="tcw", row_begin=lo, row_end=hi)
-        assert_plan_equal(mat, rp, c, v, row_begin=lo, row_end=hi)
+        mat = fx.Mat(dl, fmt="tcw", row_begin=lo, row_end=hi, tc_min_total=-1)
+        assert_plan_equal(mat, rp, c, v, row_begin=lo, row_end=hi, min_total=0)
         mat.rebuild()
-        assert_plan_equal(mat, rp, c, v, row_begin=lo, row_end=hi)
+        assert_plan_equal(mat, rp, c, v, row_begin=lo, row_end=hi, min_total=0)
         parts.append(run_spmm(mat, B, hi - lo))
         mat.free()
     assert_close(orc, gold, np.concatenate(parts), rp)
@@ -109,8 +113,8 @@ def test_dense_panel(orc):
     dl = fx.DataLoader.from_arrays(rp, c, v, k)
     B = rand_dense(n, k, 1)
     gold = orc.spmm_ref(rp, c, v, B)
-    mat = fx.Mat(dl, fmt="tcw")
-    o = assert_plan_equal(mat, rp, c, v)
+    mat = fx.Mat(dl, fmt="tcw", tc_min_total=-1)
+    o = assert_plan_equal(mat, rp, c, v, min_total=0)
     assert o["tc_ncol"][0] == 256 and o["tc_ncol"][1] == 256
     res = run_spmm(mat, B, n)
     assert_close(orc, gold, res, rp)
