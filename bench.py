@@ -29,10 +29,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default=os.environ.get("FLEX_WORKLOAD", "reddit"))
     ap.add_argument("--k", type=int, default=0)
-    ap.add_argument("--fmt", default="aspt")
+    ap.add_argument("--fmt", default="tcw", help="tcw (tensor windows + ASpT remainder, default) | aspt | csr | tile | seg | pillar")
     ap.add_argument("--tc-threshold", type=int, default=0)
     ap.add_argument("--tc-width", type=int, default=0)
     ap.add_argument("--tc-min-gain", type=int, default=0)
+    ap.add_argument("--tc-chunk-cost", type=int, default=0)
+    ap.add_argument("--tc-min-total", type=int, default=0)
     ap.add_argument("--order", default="ovo", choices=["ovo", "deg", "rcm", "gor", "dfs", "rbt"])
     ap.add_argument("--shuffle", action="store_true", help="hide the planted block order of the synthetic graph")
     ap.add_argument("--impl", default="flex_b200", choices=["flex_b200", "reference"])
@@ -49,13 +51,24 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def measured_traffic(workload, k):
+def measured_traffic(workload, k, fmt):
     """DRAM bytes per step from the committed ncu capture of this workload (profiles/r1_traffic.json)."""
     p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    key = f"{workload}:{k}" + ("" if fmt == "aspt" else f":{fmt}")
     try:
-        return json.load(open(p)).get(f"{workload}:{k}", {}).get("bytes")
+        return json.load(open(p)).get(key, {}).get("bytes")
     except Exception:
         return None
+
+
+def kernel_note(fmt, tcw):
+    tail = ("one step = all of them, timed together; the bound that binds is the L2->SM gather path (nnz*k*4 bytes), "
+            "see DESIGN.md section 5")
+    if fmt == "tcw" and tcw and tcw["ntc"]:
+        share = 100.0 * tcw["win_nnz"] / max(1, tcw["win_nnz"] + tcw["rest_nnz"])
+        return ("k_spmm_panel (remainder nz, ~55 % of the step) + k_spmm_special_cta (512-nz chunks of long rows) + "
+                f"k_spmm_tc (tcgen05 3xTF32 over the panels' shared columns, {share:.0f} % of the nz); " + tail)
+    return "k_spmm_panel (76 % of the step) + k_spmm_special_cta (512-nz chunks of long rows); " + tail
 
 
 def algorithmic_bytes(n, nnz, k):
@@ -203,6 +216,8 @@ def workload_config(args, k, n, nnz):
             "k": k, "format": args.fmt, "order": args.order, "shuffled_ids": bool(args.shuffle),
             "l2_policy": "inputs larger than L2 (A+B+C bytes > 126 MB)" if algorithmic_bytes(n, nnz, k) > 126e6
             else "whole problem fits L2: L2 flushed by a 256 MB write between timed steps",
+            "arithmetic": ("fp32 FMA for the remainder; tensor windows on tcgen05 with the 3xTF32 split (hi*hi + hi*lo + lo*hi), "
+                           "fp32 accumulate" if args.fmt == "tcw" else "fp32 FMA"),
             "parallelism": f"row-panel shards x{args.gpus}, B replicated"}
 
 
@@ -246,8 +261,9 @@ def main():
     shards = panel_shards(rp_host, world)
     lo, hi = shards[rank]
     mat = fx.Mat(dl, fmt=args.fmt, row_begin=lo, row_end=hi, tc_threshold=args.tc_threshold, tc_width=args.tc_width,
-                 tc_min_gain=args.tc_min_gain)
+                 tc_min_gain=args.tc_min_gain, tc_chunk_cost=args.tc_chunk_cost, tc_min_total=args.tc_min_total)
     tpre = [mat.tPre_ms] + [mat.rebuild() for _ in range(3)]
+    tcw = mat.tcw_info() if args.fmt == "tcw" else None
     B = synth.dense_B(n, k, device=dev)
     Cd = torch.empty((hi - lo, k), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
@@ -346,13 +362,13 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic" if args.workload != "pubmed" else "data/pubmed.csv",
             "config": workload_config(args, k, n, nnz),
             "tPre_ms": min(tpre), "tPre_over_tElap": min(tpre) / ms_per_step,
+            "tensor_windows": tcw,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "traffic": measured_traffic(args.workload, k) if (world == 1 and args.order == "ovo" and not args.shuffle and args.fmt == "aspt") else None,
+                         "traffic": measured_traffic(args.workload, k, args.fmt) if (world == 1 and args.order == "ovo" and not args.shuffle) else None,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes,
-                         "kernel": "k_spmm_panel (76 % of the step) + k_spmm_special_cta (512-nz chunks of long rows); one step = both, timed together; "
-                                   "the bound that binds is the L2->SM gather path (nnz*k*4 bytes), see DESIGN.md section 5"},
+                         "kernel": kernel_note(args.fmt, tcw)},
             "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(4 * n * k), "d2h_bytes_per_step": int(4 * (hi - lo) * k)},
             "gpu_launches": int(launches),

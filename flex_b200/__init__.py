@@ -115,7 +115,7 @@ ABI_SYMBOLS = [
     "fx_csr_from_arrays", "fx_csr_from_device", "fx_mtx_load", "fx_csr_write_csv", "fx_csr_save_bin", "fx_csr_load_bin", "fx_matrix_get_info", "fx_matrix_host_csr",
     "fx_matrix_device_csr", "fx_matrix_free", "fx_rand_B", "fx_reorder", "fx_reorder_with_rank",
     "fx_permutation", "fx_permute_rows", "fx_unpermute_rows", "fx_build", "fx_rebuild",
-    "fx_tiles_export_aspt", "fx_tiles_export_tile", "fx_tiles_export_seg", "fx_tiles_export_pillar", "fx_tiles_export_tcw", "fx_tiles_free", "fx_spmm", "fx_spmm_host", "fx_check",
+    "fx_tiles_export_aspt", "fx_tiles_export_tile", "fx_tiles_export_seg", "fx_tiles_export_pillar", "fx_tiles_export_tcw", "fx_tiles_tcw_info", "fx_tiles_free", "fx_spmm", "fx_spmm_host", "fx_check",
 ]
 
 
@@ -157,6 +157,7 @@ def lib():
     L.fx_tiles_export_seg.argtypes = [vp, C.POINTER(SegArrays)]
     L.fx_tiles_export_pillar.argtypes = [vp, C.POINTER(PillarArrays)]
     L.fx_tiles_export_tcw.argtypes = [vp, C.POINTER(TcwArrays)]
+    L.fx_tiles_tcw_info.argtypes = [vp, C.POINTER(C.c_int64)]
     L.fx_tiles_free.argtypes = [vp]
     L.fx_tiles_free.restype = None
     L.fx_spmm.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(C.c_float)]
@@ -401,6 +402,12 @@ class Mat:
                     alpha_pillar_rowPtr=_np(a.alpha_pillar_rowPtr, a.n_segs + 1, np.uint32).copy(),
                     alpha_pillarIdx=_np(a.alpha_pillarIdx, a.n_sm + 2, np.uint32).copy(),
                     segVoMap=_np(a.segVoMap, R, np.uint32).copy())
+
+    def tcw_info(self):
+        """Scalars of the tensor-window plan (no array copies)."""
+        o = (C.c_int64 * 8)()
+        _ck(lib().fx_tiles_tcw_info(self._h, o))
+        return dict(zip(("npanel", "ntc", "win_nnz", "rest_nnz", "listed_columns", "net_gain", "W", "T"), [int(x) for x in o]))
 
     def export_tcw(self):
         a = TcwArrays()

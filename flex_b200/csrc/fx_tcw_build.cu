@@ -500,3 +500,11 @@ extern "C" int fx_tiles_export_tcw(fx_tiles* t, fx_tcw_arrays* o) {
   o->rest_rowptr = w.h_rest_rowptr.data(); o->rest_col = w.h_rest_col.data(); o->rest_val = w.h_rest_val.data();
   return FX_OK;
 }
+
+extern "C" int fx_tiles_tcw_info(const fx_tiles* t, int64_t out[8]) {
+  FX_REQUIRE(t && out && t->format == FX_FMT_TCW, FX_ERR_ARG, "fx_tiles_tcw_info: not a tensor-window handle");
+  const fx_tcw_dev& w = t->tcw;
+  out[0] = t->aspt.npanel; out[1] = w.ntc; out[2] = w.win_nnz; out[3] = t->nnz_local - w.win_nnz;
+  out[4] = w.ncols_listed; out[5] = w.net_gain; out[6] = w.W; out[7] = w.T;
+  return FX_OK;
+}

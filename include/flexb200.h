@@ -199,6 +199,9 @@ int fx_tiles_export_tile(fx_tiles *t, fx_tile_arrays *out);
 int fx_tiles_export_seg(fx_tiles *t, fx_seg_arrays *out);
 int fx_tiles_export_pillar(fx_tiles *t, fx_pillar_arrays *out);
 int fx_tiles_export_tcw(fx_tiles *t, fx_tcw_arrays *out);
+/* the scalars of fx_tcw_arrays without copying any array: out = {npanel, ntc, win_nnz, rest_nnz, listed columns,
+ * net_gain, W, T} */
+int fx_tiles_tcw_info(const fx_tiles *t, int64_t out[8]);
 void fx_tiles_free(fx_tiles *t); /* Mat::freeMatGPU* mat.cuh:184-220 */
 
 /* ---- L3: SpMM ---------------------------------------------------------------------- */

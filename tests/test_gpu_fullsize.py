@@ -55,3 +55,65 @@ def test_named_shape(orc, name, k):
     assert np.array_equal(np.sort(e["perm"]), np.arange(nnz, dtype=np.int32))
     assert np.array_equal(e["csr_e"], ch[e["perm"]].astype(np.int32))
     mat.free()
+
+
+@pytest.mark.parametrize("name,k", [("reddit", 128), ("reddit", 64), ("flickr", 128)])
+def test_named_shape_tensor_windows(orc, name, k):
+    """FX_FMT_TCW at full size with its default plan: the tcgen05 window kernel + the ASpT remainder."""
+    import os
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    import tcw as tcw_oracle
+    rp, c, v = synth.generate(name, device="cuda")
+    n, nnz = rp.numel() - 1, c.numel()
+    rp32, c32 = rp.to(torch.int32), c.to(torch.int32)
+    dl = fx.DataLoader.from_device(n, nnz, rp32.data_ptr(), c32.data_ptr(), v.data_ptr(), k, name + ".csv")
+    mat = fx.Mat(dl, fmt="tcw")
+    e = mat.export_tcw()
+    if name == "reddit":
+        assert e["ntc"] > 0.9 * e["npanel"] and e["win_nnz"] > 0.2 * nnz, (e["ntc"], e["npanel"], e["win_nnz"])
+    else:
+        assert e["ntc"] == 0 and e["win_nnz"] == 0                    # the whole-matrix gate drops them
+    B = synth.dense_B(n, k, device="cuda")
+    C1 = torch.full((n, k), float("nan"), device="cuda")
+    mat.spmm(B.data_ptr(), C1.data_ptr(), k)
+    torch.cuda.synchronize()
+    # (1) sampled rows against the CPU oracle
+    rng = np.random.default_rng(1)
+    deg = (rp[1:] - rp[:-1]).cpu().numpy()
+    rows = np.unique(np.concatenate([rng.integers(0, n, 4000), np.argsort(deg)[-20:], [0, n - 1]])).astype(np.int64)
+    rph, ch, vh, Bh = rp.cpu().numpy().astype(np.uint32), c.cpu().numpy().astype(np.uint32), v.cpu().numpy(), B.cpu().numpy()
+    gold = orc.spmm_rows(rows, rph, ch, vh, Bh)
+    got = C1[torch.from_numpy(rows).cuda()].cpu().numpy()
+    sub_rp = np.concatenate([[0], np.cumsum(deg[rows])]).astype(np.uint32)
+    chk = orc.check(gold, got, sub_rp)
+    assert chk["flex_count"] == 0 and chk["aspt_pct"] < 0.01 and chk["tight_count"] == 0, chk
+    # (2) linearity: power-of-two scaling commutes with the tf32 split and with every rounding
+    B2 = B * 2
+    C2 = torch.empty_like(C1)
+    mat.spmm(B2.data_ptr(), C2.data_ptr(), k)
+    torch.cuda.synchronize()
+    assert torch.equal(C2, C1 * 2)
+    # (3) run-to-run bit identity (no atomics anywhere on the path)
+    C3 = torch.empty_like(C1)
+    mat.spmm(B.data_ptr(), C3.data_ptr(), k)
+    torch.cuda.synchronize()
+    assert torch.equal(C3, C1)
+    # (4) checksum of checksums in fp64
+    colsum_A = torch.zeros(n, dtype=torch.float64, device="cuda").index_add_(0, c, v.double())
+    lhs = C1.double().sum(0)
+    rhs = colsum_A @ B.double()
+    scale = (colsum_A.abs() @ B.double().abs()).clamp_min(1.0)
+    assert ((lhs - rhs).abs() / scale).max().item() < 1e-5
+    # (5) conservation: window part + remainder is the matrix, entry for entry
+    rp2, c2, v2 = tcw_oracle.reassemble(e)
+    assert np.array_equal(rp2, rph.astype(np.int64)) and np.array_equal(c2, ch.astype(np.int64)) and np.array_equal(v2, vh)
+    # (6) the plan against its CPU restatement on the first panels (the full plan is checked at test sizes)
+    nfirst = 128 * 24
+    sub = tcw_oracle.plan(rph[:nfirst + 1], ch[:rph[nfirst]], vh[:rph[nfirst]], min_total=0)
+    if e["ntc"]:
+        assert np.array_equal(sub["tc_cols"], e["tc_cols"][:24]) and np.array_equal(sub["tc_ncol"], e["tc_ncol"][:24])
+        assert np.array_equal(sub["win_code"], e["win_code"][:sub["win_nnz"]])
+        assert np.array_equal(sub["win_val"], e["win_val"][:sub["win_nnz"]])
+    mat.free()
