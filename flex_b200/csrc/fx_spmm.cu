@@ -426,6 +426,171 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_panel(PanelArgs a, co
 }
 
 // ---- plain CSR kernels (FX_FMT_CSR; also the fallback for k not divisible by 4) --------------
+// ---- row-grab kernel: one CTA per 128-row panel, workers take whole rows from a shared counter ----
+// Same inputs, same per-row summation order and the same finalize as k_spmm_panel, but a worker (LPR
+// lanes = one row of C) owns whole rows: it grabs the next row of the panel from a shared-memory
+// counter, streams the row's handled nz in chunks of LPR (metadata staged as (offset,value) pairs in a
+// per-worker shared buffer and read back two nz per broadcast LDS.128) and stores the row.  There is no
+// per-nz row lookup, no row-boundary path and no cross-worker partial sum, which is what the short rows
+// left over by the tensor windows need: ~3x fewer instructions per nz than the nz-balanced kernel there.
+// The 512-chunk peel bounds a row's handled length by 511 + its dense groups, and dynamic grabbing keeps
+// the workers busy behind a long row.
+template <int KC, int WARPS, bool TILES, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, const int* __restrict__ plist) {
+  constexpr int LPR = KC / 4, RPW = 32 / LPR, NW = WARPS * RPW;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // dynamic shared memory: [TILES: TS*BW*KC floats] [sbuf: NW*2*LPR uint2]
+  float* stile = reinterpret_cast<float*>(smem_raw);  // [TS][BW][KC]
+  uint2* sbuf = reinterpret_cast<uint2*>(reinterpret_cast<float*>(smem_raw) + (TILES ? (size_t)a.TS * a.BW * KC : 0));
+  __shared__ int P[BH + 1], RS[BH];
+  __shared__ int next_row;
+  __shared__ uint64_t bar;
+  auto tile = cg::tiled_partition<LPR>(cg::this_thread_block());
+  const int sl = tile.thread_rank();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / LPR;
+  const int w = warp * RPW + sub;
+  const int pslot = blockIdx.x / a.split, part_q = blockIdx.x % a.split;
+  const int p = plist ? plist[pslot] : pslot, kc0 = blockIdx.y * KC;
+  const int cnt0 = a.mcsr_cnt[p], delta = a.mcsr_cnt[p + 1] - cnt0;
+  const int ntres = TILES ? min(delta - 1, a.TS) : 0;
+  const unsigned k4 = a.k / 4;
+  const bool col_ok = kc0 / 4 + sl < (int)k4;
+  const int c4 = col_ok ? kc0 / 4 + sl : 0;
+  const int kw = min(KC, a.k - kc0);
+  const float4* B4 = reinterpret_cast<const float4*>(a.B) + c4;
+  float4* C4 = reinterpret_cast<float4*>(a.C) + c4;
+  const int BW = a.BW;
+
+  if (TILES && ntres > 0) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 32);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int* list = a.mcsr_list + (size_t)(cnt0 - p) * BW;
+      const int nslot = ntres * BW;
+      uint32_t bytes = 0;
+      for (int i = lane; i < nslot; i += 32) bytes += list[i] >= 0 ? (uint32_t)kw * 4u : 0u;
+      mbar_expect_tx_arrive(&bar, bytes);
+      for (int i = lane; i < nslot; i += 32) {
+        const int c = list[i];
+        if (c >= 0) tma_bulk_g2s(stile + (size_t)i * KC, a.B + (size_t)c * a.k + kc0, (uint32_t)kw * 4u, &bar);
+      }
+    }
+  }
+  for (int r = threadIdx.x; r < BH; r += blockDim.x) {
+    const int base = cnt0 * BH + r * delta;
+    const int rs = a.mcsr_e[base], re = a.mcsr_e[base + delta];
+    int nch = 0;
+    if (a.spec_off) nch = a.spec_off[p * BH + r + 1] - a.spec_off[p * BH + r];
+    RS[r] = rs;
+    P[r + 1] = re - rs - nch * STHRESHOLD;  // handled length; turned into a prefix below when the panel is split
+  }
+  __syncthreads();
+  int rlo = 0, rhi = BH;
+  if (a.split > 1) {  // this CTA's share of the panel: rows cut where the nz stream crosses q/split of its length
+    if (warp == 0) {
+      int v0 = P[4 * lane + 1], v1 = P[4 * lane + 2], v2 = P[4 * lane + 3], v3 = P[4 * lane + 4];
+      int s4 = v0 + v1 + v2 + v3, inc = s4;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      int ex = inc - s4;
+      if (lane == 0) P[0] = 0;
+      P[4 * lane + 1] = ex + v0; P[4 * lane + 2] = ex + v0 + v1; P[4 * lane + 3] = ex + v0 + v1 + v2; P[4 * lane + 4] = ex + s4;
+    }
+    __syncthreads();
+    const int Tall = P[BH];
+    const int tlo = (int)((long long)Tall * part_q / a.split), thi = (int)((long long)Tall * (part_q + 1) / a.split);
+    int lo = 0, hi = BH;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid] < tlo) lo = mid + 1; else hi = mid; }
+    rlo = part_q == 0 ? 0 : lo;
+    lo = 0; hi = BH;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid] < thi) lo = mid + 1; else hi = mid; }
+    rhi = part_q == a.split - 1 ? BH : lo;
+  }
+  if (threadIdx.x == 0) next_row = rlo;
+  __syncthreads();
+  if (TILES && ntres > 0) mbar_wait(&bar, 0);
+
+  const float4* S4 = reinterpret_cast<const float4*>(stile) + sl;
+  auto bload = [&](unsigned o) -> float4 {
+    if (TILES && (o & 0x80000000u)) return S4[o & 0x7fffffffu];
+    return ldg4(B4 + o);
+  };
+  uint2* sb0 = sbuf + (size_t)w * 2 * LPR;
+  int buf = 0;
+  for (;;) {
+    int r = 0;
+    if (sl == 0) r = atomicAdd(&next_row, 1);
+    r = tile.shfl(r, 0);
+    if (r >= rhi) break;
+    const int rs = RS[r];
+    const int L = a.split > 1 ? P[r + 1] - P[r] : P[r + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < L; i += LPR) {
+      const int cnt = min(LPR, L - i);
+      // lanes past the end repeat the chunk's last nz with value 0: the tail group needs no branches
+      const int e = rs + i + min(sl, cnt - 1);
+      const int c = a.csr_e[e];
+      const float v = sl < cnt ? a.csr_ev[e] : 0.f;
+      unsigned off = (unsigned)c * k4;
+      if (TILES && ntres > 0) {
+        const int base = cnt0 * BH + r * delta;
+        if (e < a.mcsr_e[base + ntres]) {
+          int g = 0;
+          for (int b = 1; b < ntres; ++b) g += e >= a.mcsr_e[base + b];
+          off = 0x80000000u | (unsigned)((g * BW + (c & (BW - 1))) * (KC / 4));
+        }
+      }
+      uint2* sb = sb0 + buf * LPR;
+      sb[sl] = make_uint2(off, __float_as_uint(v));
+      tile.sync();
+      int j = 0;
+      if (LPR >= 8) {
+        for (; j + 8 <= cnt; j += 8) {
+          const uint4 t0 = *reinterpret_cast<const uint4*>(sb + j), t1 = *reinterpret_cast<const uint4*>(sb + j + 2),
+                      t2 = *reinterpret_cast<const uint4*>(sb + j + 4), t3 = *reinterpret_cast<const uint4*>(sb + j + 6);
+          const float4 b0 = bload(t0.x), b1 = bload(t0.z), b2 = bload(t1.x), b3 = bload(t1.z), b4 = bload(t2.x),
+                       b5 = bload(t2.z), b6 = bload(t3.x), b7 = bload(t3.z);
+          fma4(acc, __uint_as_float(t0.y), b0); fma4(acc, __uint_as_float(t0.w), b1);
+          fma4(acc, __uint_as_float(t1.y), b2); fma4(acc, __uint_as_float(t1.w), b3);
+          fma4(acc, __uint_as_float(t2.y), b4); fma4(acc, __uint_as_float(t2.w), b5);
+          fma4(acc, __uint_as_float(t3.y), b6); fma4(acc, __uint_as_float(t3.w), b7);
+        }
+      }
+      for (; j < cnt; j += 4) {  // up to 3 padded nz (value 0) in the last group
+        const uint4 t0 = *reinterpret_cast<const uint4*>(sb + j), t1 = *reinterpret_cast<const uint4*>(sb + j + 2);
+        const float4 b0 = bload(t0.x), b1 = bload(t0.z), b2 = bload(t1.x), b3 = bload(t1.z);
+        fma4(acc, __uint_as_float(t0.y), b0); fma4(acc, __uint_as_float(t0.w), b1);
+        fma4(acc, __uint_as_float(t1.y), b2); fma4(acc, __uint_as_float(t1.w), b3);
+      }
+      buf ^= 1;
+    }
+    // add the row's 512-chunk partials (chunk order) and its tensor-window product, store once
+    const int row = p * BH + r;
+    if (a.spec_off) {
+      const int so = a.spec_off[row], nch = a.spec_off[row + 1] - so;
+      const float4* P4 = reinterpret_cast<const float4*>(a.partial) + (size_t)so * k4 + c4;
+      for (int c = 0; c < nch; ++c) {
+        const float4 pp = P4[(size_t)c * k4];
+        acc.x += pp.x; acc.y += pp.y; acc.z += pp.z; acc.w += pp.w;
+      }
+    }
+    if (a.tc_slot) {
+      const int ts = a.tc_slot[p];
+      if (ts >= 0) {
+        const float4 tt = ldg4(reinterpret_cast<const float4*>(a.tc_out) + ((size_t)ts * BH + r) * k4 + c4);
+        acc.x += tt.x; acc.y += tt.y; acc.z += tt.z; acc.w += tt.w;
+      }
+    }
+    if (col_ok && row < a.nloc) C4[(size_t)row * k4] = acc;
+  }
+}
+
 template <int KC>
 __global__ void __launch_bounds__(256) k_spmm_csr_vec(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col,
                                                       const float* __restrict__ val, int nrows,
@@ -520,6 +685,38 @@ static int panel_warps() {
   return w;
 }
 
+static bool use_rows_kernel() {
+  static const int v = getenv("FLEX_PANEL_KERNEL") ? atoi(getenv("FLEX_PANEL_KERNEL")) : 2;  // 1 = nz-balanced, 2 = row-grab
+  return v != 1;
+}
+
+template <int KC, int WARPS, int MINB, bool TILES>
+static int launch_one(const PanelArgs& a, const int* plist, int npan, int kchunks, size_t tile_smem, cudaStream_t s) {
+  constexpr int NW = WARPS * (32 / (KC / 4));
+  const bool rows = use_rows_kernel();
+  const size_t work = rows ? (size_t)NW * 2 * (KC / 4) * sizeof(uint2)
+                           : (size_t)2 * NW * KC * sizeof(float) + (size_t)NW * 2 * (KC / 4) * sizeof(uint2);
+  const size_t smem = tile_smem + work;
+  dim3 grid(npan * a.split, kchunks);
+  if (rows) {
+    static size_t set = 0;
+    if (smem > 48 * 1024 && smem > set) {
+      FX_CUDA(cudaFuncSetAttribute(k_spmm_rows<KC, WARPS, TILES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      set = smem;
+    }
+    k_spmm_rows<KC, WARPS, TILES, MINB><<<grid, WARPS * 32, smem, s>>>(a, plist);
+  } else {
+    static size_t set = 0;
+    if (smem > 48 * 1024 && smem > set) {
+      FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, TILES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      set = smem;
+    }
+    k_spmm_panel<KC, WARPS, TILES, MINB><<<grid, WARPS * 32, smem, s>>>(a, plist);
+  }
+  FX_LAUNCH_CHECK();
+  return FX_OK;
+}
+
 template <int KC, int WARPS, int MINB>
 static int launch_panels(const fx_aspt_dev& d, const PanelArgs& a, int kchunks, cudaStream_t s) {
   // Shared-memory staging of dense tiles only pays when a large share of the nz sits in them: the
@@ -528,39 +725,13 @@ static int launch_panels(const fx_aspt_dev& d, const PanelArgs& a, int kchunks, 
   const char* tiles_env = getenv("FLEX_TILES");  // "0" never, "1" always, unset = by density
   const double dense_frac = d.ne > 0 ? (double)(d.ne - d.S1) / d.ne : 0.0;
   const bool use_tiles = tiles_env ? atoi(tiles_env) != 0 : dense_frac >= 0.25;
-  if (!use_tiles || d.n_tiled == 0) {  // every panel through the L1 path (dense groups are ordinary nz there)
-    constexpr int NW0 = WARPS * (32 / (KC / 4));
-    const size_t ws = (size_t)2 * NW0 * KC * sizeof(float) + (size_t)NW0 * 2 * (KC / 4) * sizeof(uint2);
-    FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws));
-    dim3 grid(d.npanel * a.split, kchunks);
-    k_spmm_panel<KC, WARPS, false, MINB><<<grid, WARPS * 32, ws, s>>>(a, nullptr);
-    FX_LAUNCH_CHECK();
-    return FX_OK;
-  }
-  // per-worker partial slots + (offset,value) staging buffers
-  constexpr int NW = WARPS * (32 / (KC / 4));
-  const size_t work_smem = (size_t)2 * NW * KC * sizeof(float) + (size_t)NW * 2 * (KC / 4) * sizeof(uint2);
+  if (!use_tiles || d.n_tiled == 0)  // every panel through the L1 path (dense groups are ordinary nz there)
+    return launch_one<KC, WARPS, MINB, false>(a, nullptr, d.npanel, kchunks, 0, s);
   if (d.n_plain > 0) {
-    static bool carve = false;
-    if (!carve) {
-      FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)work_smem));
-      carve = true;
-    }
-    dim3 grid(d.n_plain * a.split, kchunks);
-    k_spmm_panel<KC, WARPS, false, MINB><<<grid, WARPS * 32, work_smem, s>>>(a, d.n_tiled ? d.plist_plain : nullptr);
-    FX_LAUNCH_CHECK();
+    const int rc = launch_one<KC, WARPS, MINB, false>(a, d.n_tiled ? d.plist_plain : nullptr, d.n_plain, kchunks, 0, s);
+    if (rc != FX_OK) return rc;
   }
-  if (d.n_tiled > 0) {
-    const size_t smem = (size_t)a.TS * a.BW * KC * sizeof(float) + work_smem;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-      FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
-    }
-    dim3 grid(d.n_tiled * a.split, kchunks);
-    k_spmm_panel<KC, WARPS, true, MINB><<<grid, WARPS * 32, smem, s>>>(a, d.plist_tiled);
-    FX_LAUNCH_CHECK();
-  }
+  if (d.n_tiled > 0) return launch_one<KC, WARPS, MINB, true>(a, d.plist_tiled, d.n_tiled, kchunks, (size_t)a.TS * a.BW * KC * sizeof(float), s);
   return FX_OK;
 }
 
