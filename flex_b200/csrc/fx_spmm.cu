@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
   float* stile = reinterpret_cast<float*>(smem_raw);  // [TS][BW][KC]
   uint2* sbuf = reinterpret_cast<uint2*>(reinterpret_cast<float*>(smem_raw) + (TILES ? (size_t)a.TS * a.BW * KC : 0));
   __shared__ int P[BH + 1], RS[BH];
-  __shared__ int next_row;
+  __shared__ int next_row, next_row2;
   __shared__ uint64_t bar;
   auto tile = cg::tiled_partition<LPR>(cg::this_thread_block());
   const int sl = tile.thread_rank();
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid] < thi) lo = mid + 1; else hi = mid; }
     rhi = part_q == a.split - 1 ? BH : lo;
   }
-  if (threadIdx.x == 0) next_row = rlo;
+  if (threadIdx.x == 0) { next_row = rlo; next_row2 = rlo; }
   __syncthreads();
   if (TILES && ntres > 0) mbar_wait(&bar, 0);
 
@@ -523,13 +523,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
   };
   uint2* sb0 = sbuf + (size_t)w * 2 * LPR;
   int buf = 0;
+  // two passes over the panel's rows, each through its own counter: the long rows first, so that no
+  // worker starts one when the others are about to run out of rows
+  constexpr int LONG_ROW = 96;
+  int pass = 0;
   for (;;) {
     int r = 0;
-    if (sl == 0) r = atomicAdd(&next_row, 1);
+    if (sl == 0) r = atomicAdd(pass == 0 ? &next_row : &next_row2, 1);
     r = tile.shfl(r, 0);
-    if (r >= rhi) break;
+    if (r >= rhi) {
+      if (pass == 1) break;
+      pass = 1;
+      continue;
+    }
     const int rs = RS[r];
     const int L = a.split > 1 ? P[r + 1] - P[r] : P[r + 1];
+    if ((L >= LONG_ROW) != (pass == 0)) continue;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = 0; i < L; i += LPR) {
       const int cnt = min(LPR, L - i);
@@ -756,7 +765,7 @@ static int launch_aspt(const fx_tiles* t, const PanelArgs& a, int special_p, cud
     case 8: return minb >= 6 ? launch_panels<KC, 8, 6>(d, a, kchunks, s) : launch_panels<KC, 8, 1>(d, a, kchunks, s);
     case 32: return launch_panels<KC, 32, 1>(d, a, kchunks, s);
     case 24: return launch_panels<KC, 24, 2>(d, a, kchunks, s);
-    default: return minb >= 3 ? launch_panels<KC, 16, 3>(d, a, kchunks, s) : launch_panels<KC, 16, 1>(d, a, kchunks, s);
+    default: return minb >= 4 ? launch_panels<KC, 16, 4>(d, a, kchunks, s) : (minb >= 3 ? launch_panels<KC, 16, 3>(d, a, kchunks, s) : launch_panels<KC, 16, 1>(d, a, kchunks, s));
   }
 }
 
