@@ -118,6 +118,14 @@ extern "C" void fx_tiles_free(fx_tiles* t) {
   if (t->ev0) cudaEventDestroy(t->ev0);
   if (t->ev1) cudaEventDestroy(t->ev1);
   if (t->own_stream) cudaStreamDestroy(t->own_stream);
+  for (int i = 0; i < 3; ++i) if (t->pipe_s[i]) cudaStreamDestroy(t->pipe_s[i]);
+  for (int i = 0; i < 8; ++i) {
+    if (t->pipe_in[i]) cudaEventDestroy(t->pipe_in[i]);
+    if (t->pipe_k0[i]) cudaEventDestroy(t->pipe_k0[i]);
+    if (t->pipe_k1[i]) cudaEventDestroy(t->pipe_k1[i]);
+  }
+  if (t->pipe_e0) cudaEventDestroy(t->pipe_e0);
+  if (t->pipe_e1) cudaEventDestroy(t->pipe_e1);
   if (t->stats_host) cudaFreeHost(t->stats_host);
   cudaFree(t->B_stage_dev); cudaFree(t->C_stage_dev);
   if (t->B_pinned) cudaFreeHost(t->B_pinned);
@@ -204,6 +212,55 @@ extern "C" int fx_spmm_host(const fx_tiles* tc, const float* B_host, float* C_ho
     FX_CUDA(cudaMalloc(&t->B_stage_dev, sizeof(float) * std::max<size_t>(nB, 1)));
     FX_CUDA(cudaMalloc(&t->C_stage_dev, sizeof(float) * std::max<size_t>(nC, 1)));
     t->stage_elems = std::max(nB, nC);
+  }
+  // Column-chunk pipeline (ASpT / tensor-window formats): the features are cut into (by default two) chunks of a multiple of 32; chunk
+  // i+1 is copied in while chunk i is multiplied and chunk i-1 is copied out (PCIe is full duplex and
+  // strided 2D copies of >= 128-byte rows run at the rate of one contiguous copy on this platform:
+  // scripts/pcie_probe.py).  The kernels take the row stride k and the chunk width separately.
+  static const int want_chunks = getenv("FLEX_HOST_CHUNKS") ? atoi(getenv("FLEX_HOST_CHUNKS")) : 2;  // measured: 4.87 ms (1), 3.92 (2), 4.53 (4) on Reddit-shape k=128
+  int nchunk = 1;
+  if ((t->format == FX_FMT_ASPT || t->format == FX_FMT_TCW) && k % 32 == 0 && k >= 64 && want_chunks > 1 &&
+      !(t->format == FX_FMT_TCW && k > t->k)) {
+    nchunk = std::min(std::min(want_chunks, k / 32), 8);
+    while ((k / 32) % nchunk) --nchunk;  // equal chunks, each a multiple of 32 features
+  }
+  if (nchunk > 1) {
+    if (!t->pipe_s[0]) {
+      for (int i = 0; i < 3; ++i) FX_CUDA(cudaStreamCreateWithFlags(&t->pipe_s[i], cudaStreamNonBlocking));
+      for (int i = 0; i < 8; ++i) {
+        FX_CUDA(cudaEventCreateWithFlags(&t->pipe_in[i], cudaEventDisableTiming));
+        FX_CUDA(cudaEventCreate(&t->pipe_k0[i]));
+        FX_CUDA(cudaEventCreate(&t->pipe_k1[i]));
+      }
+      FX_CUDA(cudaEventCreate(&t->pipe_e0));
+      FX_CUDA(cudaEventCreate(&t->pipe_e1));
+    }
+    cudaStream_t sin = t->pipe_s[0], sk = t->pipe_s[1], sout = t->pipe_s[2];
+    const int cw = k / nchunk;
+    const size_t pitch = sizeof(float) * (size_t)k, wbytes = sizeof(float) * (size_t)cw;
+    const size_t nrowsB = (size_t)t->mat->n, nrowsC = (size_t)(t->row_end - t->row_begin);
+    FX_CUDA(cudaEventRecord(t->pipe_e0, sin));
+    for (int i = 0; i < nchunk; ++i) {
+      const size_t c0 = (size_t)i * cw;
+      FX_CUDA(cudaMemcpy2DAsync(t->B_stage_dev + c0, pitch, B_host + c0, pitch, wbytes, nrowsB, cudaMemcpyHostToDevice, sin));
+      FX_CUDA(cudaEventRecord(t->pipe_in[i], sin));
+      FX_CUDA(cudaStreamWaitEvent(sk, t->pipe_in[i], 0));
+      FX_CUDA(cudaEventRecord(t->pipe_k0[i], sk));
+      int rc = fx::spmm_aspt(t, t->B_stage_dev + c0, t->C_stage_dev + c0, k, sk, cw);
+      if (rc != FX_OK) return rc;
+      FX_CUDA(cudaEventRecord(t->pipe_k1[i], sk));
+      FX_CUDA(cudaStreamWaitEvent(sout, t->pipe_k1[i], 0));
+      if (nrowsC) FX_CUDA(cudaMemcpy2DAsync(C_host + c0, pitch, t->C_stage_dev + c0, pitch, wbytes, nrowsC, cudaMemcpyDeviceToHost, sout));
+    }
+    FX_CUDA(cudaEventRecord(t->pipe_e1, sout));
+    FX_CUDA(cudaEventSynchronize(t->pipe_e1));
+    if (total_ms) FX_CUDA(cudaEventElapsedTime(total_ms, t->pipe_e0, t->pipe_e1));
+    if (tElap_ms) {
+      float sum = 0.f, ms = 0.f;
+      for (int i = 0; i < nchunk; ++i) { FX_CUDA(cudaEventElapsedTime(&ms, t->pipe_k0[i], t->pipe_k1[i])); sum += ms; }
+      *tElap_ms = sum;
+    }
+    return FX_OK;
   }
   cudaStream_t s = t->own_stream;
   cudaEvent_t e0, e1, k0, k1;

@@ -106,7 +106,8 @@ struct PanelArgs {
   const float* partial;  // [chunk][k] partial sums of the 512-chunks
   const float* B;
   float* C;
-  int npanel, nloc, k, BW, TS;
+  int npanel, nloc, k, BW, TS;  // k = row stride of B, C, partial and tc_out (floats)
+  int width;                    // feature columns computed, from the B/C pointers on (== k except in column-chunk launches)
   int split;  // CTAs per panel (>1 when the shard has too few panels to fill the GPU); cut at row boundaries
   // FX_FMT_TCW: products of the panels' tensor windows, added when a row is stored
   const float* tc_out;  // [ntc][128][k]
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special(PanelArgs a, 
   const int kc0 = blockIdx.y * KC;
   if (item >= special_p) return;  // uniform over the tile
   const unsigned k4 = a.k / 4;
-  const bool col_ok = kc0 / 4 + sl < (int)k4;
+  const bool col_ok = kc0 / 4 + sl < a.width / 4;
   const int c4 = col_ok ? kc0 / 4 + sl : 0;
   const int row = special[item], off = special2[item];
   const int p = row / BH, r = row % BH;
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special_cta(PanelArgs
   const int wk = (threadIdx.x >> 5) * RPW + (threadIdx.x & 31) / LPR;
   const int item = blockIdx.x, kc0 = blockIdx.y * KC;
   const unsigned k4 = a.k / 4;
-  const bool col_ok = kc0 / 4 + sl < (int)k4;
+  const bool col_ok = kc0 / 4 + sl < a.width / 4;
   const int c4 = col_ok ? kc0 / 4 + sl : 0;
   const int row = special[item], off = special2[item];
   const int p = row / BH, r = row % BH;
@@ -205,9 +206,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_panel(PanelArgs a, co
   const int cnt0 = a.mcsr_cnt[p], delta = a.mcsr_cnt[p + 1] - cnt0;
   const int ntres = TILES ? min(delta - 1, a.TS) : 0;  // tiles resident in shared memory
   const unsigned k4 = a.k / 4;
-  const bool col_ok = kc0 / 4 + sl < (int)k4;
+  const bool col_ok = kc0 / 4 + sl < a.width / 4;
   const int c4 = col_ok ? kc0 / 4 + sl : 0;
-  const int kw = min(KC, a.k - kc0);
+  const int kw = min(KC, a.width - kc0);
   const float4* B4 = reinterpret_cast<const float4*>(a.B) + c4;
   float4* C4 = reinterpret_cast<float4*>(a.C) + c4;
   const int BW = a.BW;
@@ -454,9 +455,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
   const int cnt0 = a.mcsr_cnt[p], delta = a.mcsr_cnt[p + 1] - cnt0;
   const int ntres = TILES ? min(delta - 1, a.TS) : 0;
   const unsigned k4 = a.k / 4;
-  const bool col_ok = kc0 / 4 + sl < (int)k4;
+  const bool col_ok = kc0 / 4 + sl < a.width / 4;
   const int c4 = col_ok ? kc0 / 4 + sl : 0;
-  const int kw = min(KC, a.k - kc0);
+  const int kw = min(KC, a.width - kc0);
   const float4* B4 = reinterpret_cast<const float4*>(a.B) + c4;
   float4* C4 = reinterpret_cast<float4*>(a.C) + c4;
   const int BW = a.BW;
@@ -747,7 +748,7 @@ static int launch_panels(const fx_aspt_dev& d, const PanelArgs& a, int kchunks, 
 template <int KC>
 static int launch_aspt(const fx_tiles* t, const PanelArgs& a, int special_p, cudaStream_t s) {
   const fx_aspt_dev& d = t->aspt;
-  const int kchunks = ceil_div(a.k, KC);
+  const int kchunks = ceil_div(a.width, KC);
   if (special_p > 0) {
     constexpr int RPW = 32 / (KC / 4);
     static const int cta_thr = getenv("FLEX_SPECIAL_CTA") ? atoi(getenv("FLEX_SPECIAL_CTA")) : 0x7fffffff;
@@ -777,16 +778,17 @@ static int launch_tc(const fxtc::TcArgs& ta, int ntc, cudaStream_t s) {
     FX_CUDA(cudaFuncSetAttribute(fxtc::k_spmm_tc<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = smem;
   }
-  dim3 grid(ntc, ceil_div(ta.k, N));
+  dim3 grid(ntc, ceil_div(ta.width, N));
   fxtc::k_spmm_tc<N><<<grid, 256, smem, s>>>(ta);
   FX_LAUNCH_CHECK();
   return FX_OK;
 }
 
-int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s) {
+int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s, int width) {
+  if (width <= 0) width = k;
   const fx_aspt_dev& d = t->aspt;
   if (d.npanel == 0) return FX_OK;
-  const int KC = pick_kc(k);
+  const int KC = pick_kc(width);
   PanelArgs a;
   a.tc_out = nullptr; a.tc_slot = nullptr;
   if (t->format == FX_FMT_TCW && t->tcw.ntc > 0) {  // tensor windows first; the panel kernel adds them in
@@ -794,7 +796,7 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
     fxtc::TcArgs ta;
     ta.win_cptr = w.win_cptr; ta.win_code = w.win_code; ta.win_val = w.win_val;
     ta.tc_panels = w.tc_panels; ta.tc_cols = w.tc_cols; ta.tc_ncol = w.tc_ncol;
-    ta.B = B; ta.out = w.tc_out; ta.k = k; ta.W = w.W;
+    ta.B = B; ta.out = w.tc_out; ta.k = k; ta.width = width; ta.W = w.W;
     const int rc = KC == 32 ? launch_tc<32>(ta, w.ntc, s) : (KC == 64 ? launch_tc<64>(ta, w.ntc, s) : launch_tc<128>(ta, w.ntc, s));
     if (rc != FX_OK) return rc;
     a.tc_out = w.tc_out; a.tc_slot = w.tc_slot;
@@ -806,13 +808,13 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   a.spec_off = special_p > 0 ? d.spec_off : nullptr;
   a.partial = d.partial;
   a.B = B; a.C = C;
-  a.npanel = d.npanel; a.nloc = t->row_end - t->row_begin; a.k = k; a.BW = d.BW;
+  a.npanel = d.npanel; a.nloc = t->row_end - t->row_begin; a.k = k; a.width = width; a.BW = d.BW;
   {  // few panels (small matrix, or a small shard of a strong-scaling run): several CTAs per panel
     static int sm = 0;
     if (!sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev); }
     const char* e = getenv("FLEX_SPLIT");
     const int want = 6 * sm;  // ~2 waves at 3 CTAs per SM
-    const int kch = ceil_div(k, KC);
+    const int kch = ceil_div(width, KC);
     int sp = e ? atoi(e) : (d.npanel * kch >= want ? 1 : ceil_div(want, d.npanel * kch));
     a.split = sp < 1 ? 1 : (sp > 8 ? 8 : sp);
   }

@@ -37,7 +37,8 @@ struct TcArgs {
   const int* tc_ncol;        // [npanel]
   const float* B;            // [ncols x k]
   float* out;                // [ntc][128][k]
-  int k, W;
+  int k, W;   // k = row stride of B and out (floats)
+  int width;  // feature columns computed, from the B/out pointers on
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
   constexpr int UNITS = 2 * N;  // (32 / 4) * (N / 4)
   constexpr int NE = 4;         // nz per thread kept in registers; longer chunks loop
   const int fq = tid % (N / 4), kq = tid / (N / 4);
-  const bool unit_ok = tid < UNITS && n0 + fq * 4 < a.k;
+  const bool unit_ok = tid < UNITS && n0 + fq * 4 < a.width;
   const float4* Bq = reinterpret_cast<const float4*>(a.B + n0 + fq * 4);
   const size_t k4 = (size_t)a.k / 4;
   float4 bx[4];
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          if (n0 + c0 + j < a.k)
+          if (n0 + c0 + j < a.width)
             *reinterpret_cast<float4*>(dst + c0 + j) =
                 make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
       }

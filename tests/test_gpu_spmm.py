@@ -231,3 +231,30 @@ def test_panel_split(orc, monkeypatch, split, k):
         mat = fx.Mat(dl, fmt="aspt", bw=128)
         assert_close(orc, gold, run_spmm(mat, B, n), rp)
         mat.free()
+
+
+@pytest.mark.parametrize("fmt", ["aspt", "tcw"])
+@pytest.mark.parametrize("k", [64, 96, 128, 256])
+def test_host_path_column_chunk_pipeline(orc, fmt, k):
+    """fx_spmm_host cuts the features into chunks of >= 32 and overlaps copy-in / multiply / copy-out: same
+    results as the oracle for every chunking (k = 96 -> 3 chunks, 256 -> 4 chunks of 64), also on a row shard."""
+    n = 1800
+    rp, c, v = random_csr(n, 7, 33, hubs=2, blocks=8)
+    dl = fx.DataLoader.from_arrays(rp, c, v, k)
+    B = rand_dense(n, k, 5)
+    gold = orc.spmm_ref(rp, c, v, B)
+    kw = dict(tc_min_total=-1) if fmt == "tcw" else {}
+    mat = fx.Mat(dl, fmt=fmt, **kw)
+    out = np.full((n, k), np.nan, np.float32)
+    res = mat.spmm_host(B, out=out)
+    assert_close(orc, gold, res, rp)
+    assert mat.last_total_ms > 0 and mat.last_tElap_ms > 0
+    res2 = mat.spmm_host(B)  # buffers and streams are reused
+    assert np.array_equal(res, res2)
+    mat.free()
+    lo, hi = 512, 1408
+    shard = fx.Mat(dl, fmt=fmt, row_begin=lo, row_end=hi, **kw)
+    part = shard.spmm_host(B)
+    sub_rp = (rp[lo:hi + 1] - rp[lo]).astype(np.uint32)
+    assert_close(orc, gold[lo:hi], part, sub_rp)
+    shard.free()
