@@ -66,9 +66,9 @@ def kernel_note(fmt, tcw):
             "see DESIGN.md section 5")
     if fmt == "tcw" and tcw and tcw["ntc"]:
         share = 100.0 * tcw["win_nnz"] / max(1, tcw["win_nnz"] + tcw["rest_nnz"])
-        return ("k_spmm_panel (remainder nz, ~55 % of the step) + k_spmm_special_cta (512-nz chunks of long rows) + "
+        return ("k_spmm_rows (remainder nz, ~50 % of the step) + k_spmm_special_cta (512-nz chunks of long rows) + "
                 f"k_spmm_tc (tcgen05 3xTF32 over the panels' shared columns, {share:.0f} % of the nz); " + tail)
-    return "k_spmm_panel (76 % of the step) + k_spmm_special_cta (512-nz chunks of long rows); " + tail
+    return "k_spmm_rows (~75 % of the step) + k_spmm_special_cta (512-nz chunks of long rows); " + tail
 
 
 def algorithmic_bytes(n, nnz, k):

@@ -65,7 +65,7 @@ extern "C" int fx_build(const fx_matrix* m, const fx_build_opts* opts, fx_tiles*
   auto fail = [&](int code) { fx_tiles_free(t); return code; };
   if (cudaEventCreate(&t->ev0) != cudaSuccess || cudaEventCreate(&t->ev1) != cudaSuccess ||
       cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMallocHost(&t->stats_host, sizeof(unsigned long long) * 8) != cudaSuccess) {
+      cudaMallocHost(&t->stats_host, sizeof(unsigned long long) * 16) != cudaSuccess) {
     fx::set_error("fx_build: event/stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(FX_ERR_CUDA);
   }

@@ -234,6 +234,55 @@ __global__ void __launch_bounds__(1024) k_panel_lists(const int* __restrict__ tc
   if (threadIdx.x == 0) stats[6] = (unsigned long long)carry_s;
 }
 
+// ---- work list of one SpMM launch: panels (all, or those of `plist`) cut into parts by their handled nz ----
+constexpr int WL_MAX_PARTS = 16;
+// mode 0: every panel; 1: the panels of `plist` = plist_plain; 2: plist_tiled (their counts come from stats[6])
+__global__ void __launch_bounds__(1024) k_worklist(const int* __restrict__ plist, int mode, const int* __restrict__ csr_v,
+                                                   const int* __restrict__ spec_off, int nr, int npanel_all,
+                                                   int2* __restrict__ wl, int cap, const unsigned long long* __restrict__ stats,
+                                                   unsigned long long* __restrict__ count) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  auto warp = cg::tiled_partition<32>(cg::this_thread_block());
+  const int n_tiled = (int)stats[6];
+  const int npan = mode == 0 ? npanel_all : (mode == 1 ? npanel_all - n_tiled : n_tiled);
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  // a part should hold about twice the average panel's handled nz (everything but the 512-chunks)
+  const long long handled_all = (long long)csr_v[nr] - (long long)STHRESHOLD * spec_off[nr];
+  const long long mean = handled_all / (npanel_all > 0 ? npanel_all : 1);
+  const long long target = mean * 2 > 4096 ? mean * 2 : 4096;
+  for (int base = 0; base < npan; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    int parts = 0, p = 0;
+    if (i < npan) {
+      p = plist ? plist[i] : i;
+      const long long h = (long long)(csr_v[(p + 1) * BH] - csr_v[p * BH]) -
+                          (long long)STHRESHOLD * (spec_off[(p + 1) * BH] - spec_off[p * BH]);
+      parts = (int)((h + target - 1) / target);
+      parts = parts < 1 ? 1 : (parts > WL_MAX_PARTS ? WL_MAX_PARTS : parts);
+    }
+    const int inc = cg::inclusive_scan(warp, parts);
+    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int ws = warp_sum[threadIdx.x];
+      const int wi = cg::inclusive_scan(warp, ws);
+      warp_sum[threadIdx.x] = wi - ws;
+    }
+    __syncthreads();
+    const int incl = carry_s + warp_sum[threadIdx.x >> 5] + inc;
+    for (int q = 0; q < parts; ++q) {
+      const int o = incl - parts + q;
+      if (o < cap) wl[o] = make_int2(p, q | (parts << 8));
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = (unsigned long long)(carry_s < cap ? carry_s : cap);
+}
+
 // ---- K4: slot lists, per-row group offsets, stable partition of the nz ---------------------
 // (key2_marking's list writes :958-959,946-949; bb_segsort#2 :1282; fill_mcsre :1006-1038;
 //  porting :1040-1048; the length statistics of cal_vari :1050-1073)
@@ -426,8 +475,10 @@ int aspt_carve(fx_tiles* t, int64_t ncols, size_t extra_bytes) {
   add(sizeof(float) * (ne + 2));                     // csr_ev
   add(sizeof(int) * (nr + 2) * 2);                   // spec_cnt, spec_off
   add(sizeof(int) * (size_t)a.special_cap * 2);
-  add(sizeof(unsigned long long) * 8);
+  add(sizeof(unsigned long long) * 16);
   add(sizeof(float) * a.partial_cap_floats);
+  a.wl_cap = (int)(npanel * 2 + ne / 4096 + 32);
+  for (int i = 0; i < 3; ++i) add(sizeof(int2) * (size_t)a.wl_cap);
   int rc = t->arena.reserve(bytes + extra_bytes);
   if (rc != FX_OK) return rc;
   Arena& A = t->arena;
@@ -452,7 +503,10 @@ int aspt_carve(fx_tiles* t, int64_t ncols, size_t extra_bytes) {
   a.spec_off = A.take<int>(nr + 2);
   a.special = A.take<int>(a.special_cap);
   a.special2 = A.take<int>(a.special_cap);
-  a.stats = A.take<unsigned long long>(8);
+  a.stats = A.take<unsigned long long>(16);
+  a.wl_all = A.take<int2>(a.wl_cap);
+  a.wl_plain = A.take<int2>(a.wl_cap);
+  a.wl_tiled = A.take<int2>(a.wl_cap);
   a.partial = A.take<float>(a.partial_cap_floats);
   if (!a.partial || !a.stats) { set_error("arena carve overflow"); return FX_ERR_NOMEM; }
   // the column counters must start at zero; every build leaves them zeroed again
@@ -470,7 +524,7 @@ int aspt_build(fx_tiles* t, cudaStream_t s) {
   const uint32_t* src_rowptr = t->src_rowptr ? t->src_rowptr : m->rowptr_dev;
   const int src_row0 = t->src_rowptr ? t->src_row0 : t->row_begin;
   const int nloc = t->row_end - t->row_begin;
-  FX_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(unsigned long long) * 8, s));
+  FX_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(unsigned long long) * 16, s));
   k_pad_rowptr<<<ceil_div(a.nr + 1, 256), 256, 0, s>>>(src_rowptr, src_row0, nloc, a.nr, a.ne, a.csr_v);
   FX_LAUNCH_CHECK();
   k_detect<<<a.npanel, 256, 0, s>>>(a.csr_v, col, min_occ, a.mcsr_chk, a.stats);
@@ -517,7 +571,15 @@ int aspt_build(fx_tiles* t, cudaStream_t s) {
   FX_LAUNCH_CHECK();
   k_fill_special<<<ceil_div(a.nr, 256), 256, 0, s>>>(a.spec_cnt, a.spec_off, a.nr, a.special, a.special2);
   FX_LAUNCH_CHECK();
-  FX_CUDA(cudaMemcpyAsync(t->stats_host, a.stats, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
+  k_worklist<<<1, 1024, 0, s>>>(nullptr, 0, a.csr_v, a.spec_off, a.nr, a.npanel, a.wl_all, a.wl_cap, a.stats, a.stats + 8);
+  FX_LAUNCH_CHECK();
+  if (a.any_flag) {  // the tiled launch and the plain launch walk their own panel lists (counts are on the device)
+    k_worklist<<<1, 1024, 0, s>>>(a.plist_plain, 1, a.csr_v, a.spec_off, a.nr, a.npanel, a.wl_plain, a.wl_cap, a.stats, a.stats + 9);
+    FX_LAUNCH_CHECK();
+    k_worklist<<<1, 1024, 0, s>>>(a.plist_tiled, 2, a.csr_v, a.spec_off, a.nr, a.npanel, a.wl_tiled, a.wl_cap, a.stats, a.stats + 10);
+    FX_LAUNCH_CHECK();
+  }
+  FX_CUDA(cudaMemcpyAsync(t->stats_host, a.stats, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, s));
   FX_CUDA(cudaStreamSynchronize(s));
   a.S1 = (long long)t->stats_host[0];
   a.S2 = (long long)t->stats_host[1];
@@ -526,6 +588,9 @@ int aspt_build(fx_tiles* t, cudaStream_t s) {
   a.max_tp = a.any_flag ? (int)t->stats_host[5] : 0;
   a.n_tiled = a.any_flag ? (int)t->stats_host[6] : 0;
   a.n_plain = a.npanel - a.n_tiled;
+  a.n_wl_all = (int)t->stats_host[8];
+  a.n_wl_plain = a.any_flag ? (int)t->stats_host[9] : 0;
+  a.n_wl_tiled = a.any_flag ? (int)t->stats_host[10] : 0;
   a.avg = a.nr ? (double)a.S1 / a.nr : 0;                       // :1226 / :1300
   a.vari = a.nr ? (double)a.S2 / a.nr - a.avg * a.avg : 0;      // Σ(len-avg)²/nr, exact sums
   const int nc = a.n;

@@ -112,6 +112,10 @@ struct fx_aspt_dev {  // device-side ASpT format (aspt/sspmm_128.cu:76-90 global
   int *spec_cnt = nullptr, *spec_off = nullptr, *special = nullptr, *special2 = nullptr;
   int *plist_plain = nullptr, *plist_tiled = nullptr;  // panels without / with dense tiles (ascending)
   int n_plain = 0, n_tiled = 0;
+  // work lists of the SpMM launches: one entry per CTA = (panel, part | parts << 8); a panel with several times
+  // the average work is cut into up to 16 parts at row boundaries (skewed orderings put all hubs in a few panels)
+  int2 *wl_all = nullptr, *wl_plain = nullptr, *wl_tiled = nullptr;
+  int n_wl_all = 0, n_wl_plain = 0, n_wl_tiled = 0, wl_cap = 0;
   unsigned long long* stats = nullptr;  // [0]=S1 [1]=S2 [2]=special chunks [3]=num_dense [4]=any flag
   float* partial = nullptr;             // special_p_cap x k partial sums of 512-chunks
   size_t partial_cap_floats = 0;
@@ -128,7 +132,7 @@ struct fx_aspt_dev {  // device-side ASpT format (aspt/sspmm_128.cu:76-90 global
 };
 
 struct fx_tcw_dev {  // tensor-window format (fx_tcw_build.cu): per-panel column lists + window nz + remainder CSR
-  int T = 4, W = 512, min_gain = 1024, chunk_cost = 224;
+  int T = 4, W = 256, min_gain = 1024, chunk_cost = 224;
   long long min_total = 1000000, net_gain = 0;
   int *tc_cols = nullptr, *tc_ncol = nullptr, *tc_slot = nullptr, *tc_panels = nullptr;
   int *csr_v = nullptr, *win_len = nullptr, *win_rowptr = nullptr, *chunk_len = nullptr, *win_cptr = nullptr;

@@ -109,6 +109,7 @@ struct PanelArgs {
   int npanel, nloc, k, BW, TS;  // k = row stride of B, C, partial and tc_out (floats)
   int width;                    // feature columns computed, from the B/C pointers on (== k except in column-chunk launches)
   int split;  // CTAs per panel (>1 when the shard has too few panels to fill the GPU); cut at row boundaries
+  const int2* wl;  // per-CTA work list (panel, part | parts << 8) of the row kernel; nullptr = blockIdx.x / split
   // FX_FMT_TCW: products of the panels' tensor windows, added when a row is stored
   const float* tc_out;  // [ntc][128][k]
   const int* tc_slot;   // [npanel] position in tc_out or -1; nullptr = no windows
@@ -174,271 +175,24 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special_cta(PanelArgs
   }
 }
 
-// ---- panel kernel: one CTA per 128-row panel, nz-balanced inside the CTA ----------------------
-// The panel's handled nz (every row's [dense groups | sparse tail], i.e. everything except the
-// 512-chunks k_spmm_special takes from the END of long sparse groups) form one logical stream of
-// T nz.  The CTA's NW workers (a worker = LPR lanes = one row of C at a time) each take T/NW
-// consecutive nz of that stream, whatever rows they fall in: no warp idles behind a long row and
-// every worker issues long runs of independent 128-bit B loads.  Rows are looked up through a
-// 129-entry prefix table in shared memory.  A row that lies inside one worker's range is stored
-// directly; the (at most two) rows a worker shares with its neighbours are reduced through a
-// shared-memory slot in worker order, so every C element is still written once, deterministically.
-// TILES=false: panels without a dense tile -- no dynamic shared memory, the SM keeps its L1.
+// ---- row-grab kernel: one CTA per 128-row panel, workers take whole rows from a shared counter ----
+// The panel's handled nz are every row's [dense groups | sparse tail], i.e. everything except the
+// 512-chunks k_spmm_special takes from the END of long sparse groups.  A worker (LPR lanes = one row of
+// C, each lane a float4 of features) owns whole rows: it grabs the next row of the panel from a
+// shared-memory counter (long rows in a first pass, so none starts when the others run out), streams
+// the row's nz in chunks of LPR -- metadata staged as (offset,value) pairs in a per-worker shared
+// buffer and read back two nz per broadcast LDS.128, B rows fetched with 128-bit loads, FFMA2 -- adds
+// the row's 512-chunk partials and its tensor-window product and stores the row once: every C element
+// is written exactly once, in a fixed summation order, without atomics.
+// (Round-1 history: an nz-balanced variant -- workers take equal slices of the panel's nz stream, rows
+// looked up per nz through a prefix table, shared rows reduced through shared memory -- needed ~3x the
+// instructions per nz on short rows: 0.729 ms vs 0.634 ms on Reddit-shape)
+// TILES=false: no dynamic shared memory beyond the staging buffers, the SM keeps its L1.
 // TILES=true : the first TS dense tiles of the panel are TMA-staged in shared memory; nz of those
 //              tiles read B from there, all other nz (further tiles, sparse tail) from L1/L2.
 template <int KC, int WARPS, bool TILES, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_panel(PanelArgs a, const int* __restrict__ plist) {
-  constexpr int LPR = KC / 4, RPW = 32 / LPR, NW = WARPS * RPW;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // dynamic shared memory: [TILES: TS*BW*KC floats] [part: 2*NW*KC floats] [sbuf: NW*2*LPR uint2]
-  float* stile = reinterpret_cast<float*>(smem_raw);  // [TS][BW][KC]
-  float* part = reinterpret_cast<float*>(smem_raw) + (TILES ? (size_t)a.TS * a.BW * KC : 0);  // [2][NW][KC]
-  uint2* sbuf = reinterpret_cast<uint2*>(part + 2 * NW * KC);                                   // [NW][2][LPR]
-  __shared__ int P[BH + 1], RS[BH];
-  __shared__ int head_row[NW], tail_row[NW], head_end[NW], w_empty[NW];
-  __shared__ uint64_t bar;
-  auto tile = cg::tiled_partition<LPR>(cg::this_thread_block());
-  const int sl = tile.thread_rank();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / LPR;
-  const int w = warp * RPW + sub;
-  const int pslot = blockIdx.x / a.split, part_q = blockIdx.x % a.split;
-  const int p = plist ? plist[pslot] : pslot, kc0 = blockIdx.y * KC;
-  const int cnt0 = a.mcsr_cnt[p], delta = a.mcsr_cnt[p + 1] - cnt0;
-  const int ntres = TILES ? min(delta - 1, a.TS) : 0;  // tiles resident in shared memory
-  const unsigned k4 = a.k / 4;
-  const bool col_ok = kc0 / 4 + sl < a.width / 4;
-  const int c4 = col_ok ? kc0 / 4 + sl : 0;
-  const int kw = min(KC, a.width - kc0);
-  const float4* B4 = reinterpret_cast<const float4*>(a.B) + c4;
-  float4* C4 = reinterpret_cast<float4*>(a.C) + c4;
-  const int BW = a.BW;
-
-  if (TILES && ntres > 0) {
-    if (threadIdx.x == 0) {
-      mbar_init(&bar, 32);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (warp == 0) {  // producer: one bulk copy per occupied slot; each lane announces its bytes first
-      const int* list = a.mcsr_list + (size_t)(cnt0 - p) * BW;
-      const int nslot = ntres * BW;
-      uint32_t bytes = 0;
-      for (int i = lane; i < nslot; i += 32) bytes += list[i] >= 0 ? (uint32_t)kw * 4u : 0u;
-      mbar_expect_tx_arrive(&bar, bytes);
-      for (int i = lane; i < nslot; i += 32) {
-        const int c = list[i];
-        if (c >= 0) tma_bulk_g2s(stile + (size_t)i * KC, a.B + (size_t)c * a.k + kc0, (uint32_t)kw * 4u, &bar);
-      }
-    }
-  }
-  // row table: RS[r] = first handled nz, P = exclusive prefix of handled lengths
-  for (int r = threadIdx.x; r < BH; r += blockDim.x) {
-    const int base = cnt0 * BH + r * delta;
-    const int rs = a.mcsr_e[base], re = a.mcsr_e[base + delta];
-    int nch = 0;
-    if (a.spec_off) nch = a.spec_off[p * BH + r + 1] - a.spec_off[p * BH + r];
-    RS[r] = rs;
-    P[r + 1] = re - rs - nch * STHRESHOLD;
-  }
-  if (threadIdx.x < NW) { head_row[threadIdx.x] = -1; tail_row[threadIdx.x] = -1; head_end[threadIdx.x] = 0; w_empty[threadIdx.x] = 1; }
-  __syncthreads();
-  if (warp == 0) {
-    int v0 = P[4 * lane + 1], v1 = P[4 * lane + 2], v2 = P[4 * lane + 3], v3 = P[4 * lane + 4];
-    int s = v0 + v1 + v2 + v3, inc = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    int ex = inc - s;
-    if (lane == 0) P[0] = 0;
-    P[4 * lane + 1] = ex + v0; P[4 * lane + 2] = ex + v0 + v1; P[4 * lane + 3] = ex + v0 + v1 + v2; P[4 * lane + 4] = ex + s;
-  }
-  __syncthreads();
-  // this CTA's share of the panel: rows [rlo, rhi), cut where the stream crosses q/split of its length
-  int rlo = 0, rhi = BH;
-  if (a.split > 1) {
-    const int Tall = P[BH];
-    const int tlo = (int)((long long)Tall * part_q / a.split), thi = (int)((long long)Tall * (part_q + 1) / a.split);
-    int lo = 0, hi = BH;  // first r with P[r] >= tlo
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid] < tlo) lo = mid + 1; else hi = mid; }
-    rlo = part_q == 0 ? 0 : lo;
-    lo = 0; hi = BH;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid] < thi) lo = mid + 1; else hi = mid; }
-    rhi = part_q == a.split - 1 ? BH : lo;
-  }
-  const int T0 = P[rlo], T = P[rhi] - T0;
-
-  auto finalize = [&](int r, float4 acc) {  // add the row's 512-chunk partials (chunk order) and store
-    const int row = p * BH + r;
-    if (a.spec_off) {
-      const int so = a.spec_off[row], nch = a.spec_off[row + 1] - so;
-      const float4* P4 = reinterpret_cast<const float4*>(a.partial) + (size_t)so * k4 + c4;
-      for (int c = 0; c < nch; ++c) {
-        const float4 pp = P4[(size_t)c * k4];
-        acc.x += pp.x; acc.y += pp.y; acc.z += pp.z; acc.w += pp.w;
-      }
-    }
-    if (a.tc_slot) {
-      const int ts = a.tc_slot[p];
-      if (ts >= 0) {
-        const float4 tt = ldg4(reinterpret_cast<const float4*>(a.tc_out) + ((size_t)ts * BH + r) * k4 + c4);
-        acc.x += tt.x; acc.y += tt.y; acc.z += tt.z; acc.w += tt.w;
-      }
-    }
-    if (col_ok && row < a.nloc) C4[(size_t)row * k4] = acc;
-  };
-
-  // rows without any handled nz (empty, or consumed entirely by 512-chunks)
-  for (int idx = threadIdx.x; idx < BH * LPR; idx += blockDim.x) {
-    const int r = idx / LPR;  // idx % LPR == sl because blockDim is a multiple of LPR
-    if (r >= rlo && r < rhi && P[r + 1] == P[r]) finalize(r, make_float4(0.f, 0.f, 0.f, 0.f));
-  }
-
-  const int a_pos = T0 + (int)((long long)T * w / NW), b_pos = T0 + (int)((long long)T * (w + 1) / NW);
-  if (TILES && ntres > 0) mbar_wait(&bar, 0);
-
-  if (a_pos < b_pos) {
-    if (sl == 0) w_empty[w] = 0;
-    int cur = -1;
-    bool cur_started = false;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* S4 = reinterpret_cast<const float4*>(stile) + sl;
-
-    auto load_chunk = [&](int q0, unsigned& off, float& v, int& rrow, bool& st) {
-      const int q = q0 + sl;
-      off = 0; v = 0.f; rrow = 0; st = false;
-      if (q < b_pos) {
-        int lo = 0, hi = BH;  // largest r with P[r] <= q
-#pragma unroll
-        for (int it = 0; it < 7; ++it) {
-          const int mid = (lo + hi) >> 1;
-          if (P[mid] <= q) lo = mid; else hi = mid;
-        }
-        const int e = RS[lo] + (q - P[lo]);
-        const int c = a.csr_e[e];
-        v = a.csr_ev[e];
-        rrow = lo;
-        st = q == P[lo];
-        off = (unsigned)c * k4;
-        if (TILES && ntres > 0) {
-          const int base = cnt0 * BH + lo * delta;
-          if (e < a.mcsr_e[base + ntres]) {
-            int g = 0;
-            for (int b = 1; b < ntres; ++b) g += e >= a.mcsr_e[base + b];
-            off = 0x80000000u | (unsigned)((g * BW + (c & (BW - 1))) * (KC / 4));
-          }
-        }
-      }
-    };
-    auto bload = [&](unsigned o) -> float4 {
-      if (TILES && (o & 0x80000000u)) return S4[o & 0x7fffffffu];
-      return ldg4(B4 + o);
-    };
-    auto row_ended = [&]() {  // the pending row `cur` has no more nz in this worker's range
-      if (cur_started) finalize(cur, acc);
-      else {
-        reinterpret_cast<float4*>(part + (size_t)w * KC)[sl] = acc;
-        if (sl == 0) { head_row[w] = cur; head_end[w] = 1; }
-      }
-    };
-
-    // (offset,value) pairs of a chunk are staged in a per-worker shared buffer (double buffered) and
-    // read back two nz at a time with one broadcast LDS.128 -- 0.5 instruction per nz instead of two
-    // shuffles.
-    uint2* sb0 = sbuf + (size_t)w * 2 * LPR;
-    unsigned n_off; float n_v; int n_row; bool n_st;
-    load_chunk(a_pos, n_off, n_v, n_row, n_st);
-    sb0[sl] = make_uint2(n_off, __float_as_uint(n_v));
-    tile.sync();
-    int buf = 0;
-    for (int q0 = a_pos; q0 < b_pos; q0 += LPR) {
-      const int rrow = n_row; const bool st = n_st;
-      const uint2* sb = sb0 + buf * LPR;
-      if (q0 + LPR < b_pos) {
-        load_chunk(q0 + LPR, n_off, n_v, n_row, n_st);
-        sb0[(buf ^ 1) * LPR + sl] = make_uint2(n_off, __float_as_uint(n_v));
-      }
-      const int cnt = min(LPR, b_pos - q0);
-      const unsigned smask = tile.ballot(st);
-      if (cur < 0 && !(smask & 1u)) { cur = tile.shfl(rrow, 0); cur_started = false; }
-      if (smask == 0u && cnt == LPR) {  // whole chunk inside the current row: straight-line code
-#pragma unroll
-        for (int j = 0; j < LPR; j += 8) {
-          const uint4 t0 = *reinterpret_cast<const uint4*>(sb + j), t1 = *reinterpret_cast<const uint4*>(sb + j + 2),
-                      t2 = *reinterpret_cast<const uint4*>(sb + j + 4), t3 = *reinterpret_cast<const uint4*>(sb + j + 6);
-          const float4 b0 = bload(t0.x), b1 = bload(t0.z), b2 = bload(t1.x), b3 = bload(t1.z), b4 = bload(t2.x),
-                       b5 = bload(t2.z), b6 = bload(t3.x), b7 = bload(t3.z);
-          fma4(acc, __uint_as_float(t0.y), b0); fma4(acc, __uint_as_float(t0.w), b1);
-          fma4(acc, __uint_as_float(t1.y), b2); fma4(acc, __uint_as_float(t1.w), b3);
-          fma4(acc, __uint_as_float(t2.y), b4); fma4(acc, __uint_as_float(t2.w), b5);
-          fma4(acc, __uint_as_float(t3.y), b6); fma4(acc, __uint_as_float(t3.w), b7);
-        }
-      } else {
-        int j = 0;
-        while (j < cnt) {
-          if (j + 4 <= cnt && ((smask >> j) & 0xFu) == 0u && (j & 1) == 0) {
-            const uint4 t0 = *reinterpret_cast<const uint4*>(sb + j), t1 = *reinterpret_cast<const uint4*>(sb + j + 2);
-            const float4 b0 = bload(t0.x), b1 = bload(t0.z), b2 = bload(t1.x), b3 = bload(t1.z);
-            fma4(acc, __uint_as_float(t0.y), b0); fma4(acc, __uint_as_float(t0.w), b1);
-            fma4(acc, __uint_as_float(t1.y), b2); fma4(acc, __uint_as_float(t1.w), b3);
-            j += 4;
-            continue;
-          }
-          if ((smask >> j) & 1u) {
-            if (cur >= 0) row_ended();
-            cur = tile.shfl(rrow, j);
-            cur_started = true;
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          const uint2 t = sb[j];
-          fma4(acc, __uint_as_float(t.y), bload(t.x));
-          ++j;
-        }
-      }
-      tile.sync();
-      buf ^= 1;
-    }
-    // the row in progress at the end of the range
-    const bool ended = b_pos == P[cur + 1];
-    if (cur_started && ended) finalize(cur, acc);
-    else if (cur_started) {
-      reinterpret_cast<float4*>(part + (size_t)(NW + w) * KC)[sl] = acc;
-      if (sl == 0) tail_row[w] = cur;
-    } else {
-      reinterpret_cast<float4*>(part + (size_t)w * KC)[sl] = acc;
-      if (sl == 0) { head_row[w] = cur; head_end[w] = ended ? 1 : 0; }
-    }
-  }
-  __syncthreads();
-  // rows shared between workers: the worker holding the row's beginning sums the chain in order
-  const int tr = tail_row[w];
-  if (tr >= 0) {
-    float4 tot = reinterpret_cast<const float4*>(part + (size_t)(NW + w) * KC)[sl];
-    for (int w2 = w + 1; w2 < NW; ++w2) {
-      if (w_empty[w2]) continue;
-      if (head_row[w2] != tr) break;
-      const float4 h = reinterpret_cast<const float4*>(part + (size_t)w2 * KC)[sl];
-      tot.x += h.x; tot.y += h.y; tot.z += h.z; tot.w += h.w;
-      if (head_end[w2]) break;
-    }
-    finalize(tr, tot);
-  }
-}
-
-// ---- plain CSR kernels (FX_FMT_CSR; also the fallback for k not divisible by 4) --------------
-// ---- row-grab kernel: one CTA per 128-row panel, workers take whole rows from a shared counter ----
-// Same inputs, same per-row summation order and the same finalize as k_spmm_panel, but a worker (LPR
-// lanes = one row of C) owns whole rows: it grabs the next row of the panel from a shared-memory
-// counter, streams the row's handled nz in chunks of LPR (metadata staged as (offset,value) pairs in a
-// per-worker shared buffer and read back two nz per broadcast LDS.128) and stores the row.  There is no
-// per-nz row lookup, no row-boundary path and no cross-worker partial sum, which is what the short rows
-// left over by the tensor windows need: ~3x fewer instructions per nz than the nz-balanced kernel there.
-// The 512-chunk peel bounds a row's handled length by 511 + its dense groups, and dynamic grabbing keeps
-// the workers busy behind a long row.
-template <int KC, int WARPS, bool TILES, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, const int* __restrict__ plist) {
-  constexpr int LPR = KC / 4, RPW = 32 / LPR, NW = WARPS * RPW;
+  constexpr int LPR = KC / 4, RPW = 32 / LPR;  // NW = WARPS * RPW workers per CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // dynamic shared memory: [TILES: TS*BW*KC floats] [sbuf: NW*2*LPR uint2]
   float* stile = reinterpret_cast<float*>(smem_raw);  // [TS][BW][KC]
@@ -450,8 +204,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
   const int sl = tile.thread_rank();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / LPR;
   const int w = warp * RPW + sub;
-  const int pslot = blockIdx.x / a.split, part_q = blockIdx.x % a.split;
-  const int p = plist ? plist[pslot] : pslot, kc0 = blockIdx.y * KC;
+  int p, part_q, split;
+  if (a.wl) {
+    const int2 e = a.wl[blockIdx.x];
+    p = e.x; part_q = e.y & 0xff; split = e.y >> 8;
+  } else {
+    const int pslot = blockIdx.x / a.split;
+    part_q = blockIdx.x % a.split; split = a.split;
+    p = plist ? plist[pslot] : pslot;
+  }
+  const int kc0 = blockIdx.y * KC;
   const int cnt0 = a.mcsr_cnt[p], delta = a.mcsr_cnt[p + 1] - cnt0;
   const int ntres = TILES ? min(delta - 1, a.TS) : 0;
   const unsigned k4 = a.k / 4;
@@ -490,7 +252,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
   }
   __syncthreads();
   int rlo = 0, rhi = BH;
-  if (a.split > 1) {  // this CTA's share of the panel: rows cut where the nz stream crosses q/split of its length
+  if (split > 1) {  // this CTA's share of the panel: rows cut where the nz stream crosses q/split of its length
     if (warp == 0) {
       int v0 = P[4 * lane + 1], v1 = P[4 * lane + 2], v2 = P[4 * lane + 3], v3 = P[4 * lane + 4];
       int s4 = v0 + v1 + v2 + v3, inc = s4;
@@ -505,13 +267,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
     }
     __syncthreads();
     const int Tall = P[BH];
-    const int tlo = (int)((long long)Tall * part_q / a.split), thi = (int)((long long)Tall * (part_q + 1) / a.split);
+    const int tlo = (int)((long long)Tall * part_q / split), thi = (int)((long long)Tall * (part_q + 1) / split);
     int lo = 0, hi = BH;
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid] < tlo) lo = mid + 1; else hi = mid; }
     rlo = part_q == 0 ? 0 : lo;
     lo = 0; hi = BH;
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid] < thi) lo = mid + 1; else hi = mid; }
-    rhi = part_q == a.split - 1 ? BH : lo;
+    rhi = part_q == split - 1 ? BH : lo;
   }
   if (threadIdx.x == 0) { next_row = rlo; next_row2 = rlo; }
   __syncthreads();
@@ -538,7 +300,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
       continue;
     }
     const int rs = RS[r];
-    const int L = a.split > 1 ? P[r + 1] - P[r] : P[r + 1];
+    const int L = split > 1 ? P[r + 1] - P[r] : P[r + 1];
     if ((L >= LONG_ROW) != (pass == 0)) continue;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = 0; i < L; i += LPR) {
@@ -695,34 +457,21 @@ static int panel_warps() {
   return w;
 }
 
-static bool use_rows_kernel() {
-  static const int v = getenv("FLEX_PANEL_KERNEL") ? atoi(getenv("FLEX_PANEL_KERNEL")) : 2;  // 1 = nz-balanced, 2 = row-grab
-  return v != 1;
-}
-
 template <int KC, int WARPS, int MINB, bool TILES>
-static int launch_one(const PanelArgs& a, const int* plist, int npan, int kchunks, size_t tile_smem, cudaStream_t s) {
+static int launch_one(PanelArgs a, const int* plist, int npan, const int2* wl, int nwl, int kchunks, size_t tile_smem,
+                      cudaStream_t s) {
   constexpr int NW = WARPS * (32 / (KC / 4));
-  const bool rows = use_rows_kernel();
-  const size_t work = rows ? (size_t)NW * 2 * (KC / 4) * sizeof(uint2)
-                           : (size_t)2 * NW * KC * sizeof(float) + (size_t)NW * 2 * (KC / 4) * sizeof(uint2);
-  const size_t smem = tile_smem + work;
-  dim3 grid(npan * a.split, kchunks);
-  if (rows) {
-    static size_t set = 0;
-    if (smem > 48 * 1024 && smem > set) {
-      FX_CUDA(cudaFuncSetAttribute(k_spmm_rows<KC, WARPS, TILES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      set = smem;
-    }
-    k_spmm_rows<KC, WARPS, TILES, MINB><<<grid, WARPS * 32, smem, s>>>(a, plist);
-  } else {
-    static size_t set = 0;
-    if (smem > 48 * 1024 && smem > set) {
-      FX_CUDA(cudaFuncSetAttribute(k_spmm_panel<KC, WARPS, TILES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      set = smem;
-    }
-    k_spmm_panel<KC, WARPS, TILES, MINB><<<grid, WARPS * 32, smem, s>>>(a, plist);
+  const size_t smem = tile_smem + (size_t)NW * 2 * (KC / 4) * sizeof(uint2);  // + per-worker (offset,value) staging
+  static const bool no_wl = getenv("FLEX_NO_WORKLIST") != nullptr;
+  // a uniform split (few panels, or FLEX_SPLIT) keeps the blockIdx mapping; otherwise the build's work list
+  a.wl = (a.split == 1 && wl && nwl > 0 && !no_wl) ? wl : nullptr;
+  dim3 grid(a.wl ? nwl : npan * a.split, kchunks);
+  static size_t set = 0;
+  if (smem > 48 * 1024 && smem > set) {
+    FX_CUDA(cudaFuncSetAttribute(k_spmm_rows<KC, WARPS, TILES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set = smem;
   }
+  k_spmm_rows<KC, WARPS, TILES, MINB><<<grid, WARPS * 32, smem, s>>>(a, plist);
   FX_LAUNCH_CHECK();
   return FX_OK;
 }
@@ -736,12 +485,13 @@ static int launch_panels(const fx_aspt_dev& d, const PanelArgs& a, int kchunks, 
   const double dense_frac = d.ne > 0 ? (double)(d.ne - d.S1) / d.ne : 0.0;
   const bool use_tiles = tiles_env ? atoi(tiles_env) != 0 : dense_frac >= 0.25;
   if (!use_tiles || d.n_tiled == 0)  // every panel through the L1 path (dense groups are ordinary nz there)
-    return launch_one<KC, WARPS, MINB, false>(a, nullptr, d.npanel, kchunks, 0, s);
+    return launch_one<KC, WARPS, MINB, false>(a, nullptr, d.npanel, d.wl_all, d.n_wl_all, kchunks, 0, s);
   if (d.n_plain > 0) {
-    const int rc = launch_one<KC, WARPS, MINB, false>(a, d.n_tiled ? d.plist_plain : nullptr, d.n_plain, kchunks, 0, s);
+    const int rc = launch_one<KC, WARPS, MINB, false>(a, d.n_tiled ? d.plist_plain : nullptr, d.n_plain, d.wl_plain, d.n_wl_plain, kchunks, 0, s);
     if (rc != FX_OK) return rc;
   }
-  if (d.n_tiled > 0) return launch_one<KC, WARPS, MINB, true>(a, d.plist_tiled, d.n_tiled, kchunks, (size_t)a.TS * a.BW * KC * sizeof(float), s);
+  if (d.n_tiled > 0)
+    return launch_one<KC, WARPS, MINB, true>(a, d.plist_tiled, d.n_tiled, d.wl_tiled, d.n_wl_tiled, kchunks, (size_t)a.TS * a.BW * KC * sizeof(float), s);
   return FX_OK;
 }
 
@@ -790,7 +540,7 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   if (d.npanel == 0) return FX_OK;
   const int KC = pick_kc(width);
   PanelArgs a;
-  a.tc_out = nullptr; a.tc_slot = nullptr;
+  a.tc_out = nullptr; a.tc_slot = nullptr; a.wl = nullptr;
   if (t->format == FX_FMT_TCW && t->tcw.ntc > 0) {  // tensor windows first; the panel kernel adds them in
     const fx_tcw_dev& w = t->tcw;
     fxtc::TcArgs ta;

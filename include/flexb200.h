@@ -71,7 +71,7 @@ typedef struct {
   int32_t cmajor;     /* FX_FMT_TILE: 0 = csr2flex_Rmajor, 1 = csr2flex_Cmajor (COL_MAJ_TILE, DataLoader.cuh:18) */
   /* FX_FMT_TCW plan (flex_b200/csrc/fx_tcw_build.cu has the rule); 0 = default; negative tc_min_* = "no minimum" */
   int32_t tc_threshold;  /* a column is a candidate with >= this many nz in the panel (4) */
-  int32_t tc_width;      /* at most this many window columns per panel, multiple of 32 (512) */
+  int32_t tc_width;      /* at most this many window columns per panel, multiple of 32 (256) */
   int32_t tc_min_gain;   /* a panel keeps its window only if its net gain, in B-row fetches, reaches this (1024) */
   int32_t tc_chunk_cost; /* what one 32-column chunk costs, in B-row fetches (224) */
   int32_t tc_min_total;  /* the matrix keeps its windows only if the summed net gain reaches this (1000000) */

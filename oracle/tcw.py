@@ -52,7 +52,7 @@ def select_columns(panel_cols, T, W, min_gain, chunk_cost):
     return np.sort(cu[order[:min(m, 32 * nch)]]), gain
 
 
-def plan(rowptr, col, val, T=4, W=512, min_gain=1024, chunk_cost=224, min_total=1000000, row_begin=0, row_end=None):
+def plan(rowptr, col, val, T=4, W=256, min_gain=1024, chunk_cost=224, min_total=1000000, row_begin=0, row_end=None):
     rowptr = np.asarray(rowptr, np.int64)
     n_all = rowptr.size - 1
     row_end = n_all if row_end is None or (row_begin == 0 and row_end == 0) else row_end
