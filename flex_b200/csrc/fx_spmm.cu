@@ -559,13 +559,14 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   a.partial = d.partial;
   a.B = B; a.C = C;
   a.npanel = d.npanel; a.nloc = t->row_end - t->row_begin; a.k = k; a.width = width; a.BW = d.BW;
-  {  // few panels (small matrix, or a small shard of a strong-scaling run): several CTAs per panel
+  {  // fewer panels than SMs: several CTAs per panel.  Otherwise one CTA per work-list entry -- the row kernel
+     // balances inside a panel by itself, and more CTAs only repeat its prologue (measured: flickr-shape 0.103 ms
+     // unsplit vs 0.121 split in two; 1/8 Reddit-shape shards 0.136 / 0.129 / 0.141 / 0.146 ms for 1 / 2 / 3 / 4)
     static int sm = 0;
     if (!sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev); }
     const char* e = getenv("FLEX_SPLIT");
-    const int want = 6 * sm;  // ~2 waves at 3 CTAs per SM
     const int kch = ceil_div(width, KC);
-    int sp = e ? atoi(e) : (d.npanel * kch >= want ? 1 : ceil_div(want, d.npanel * kch));
+    int sp = e ? atoi(e) : (d.npanel * kch >= sm ? 1 : ceil_div(2 * sm, d.npanel * kch));
     a.split = sp < 1 ? 1 : (sp > 8 ? 8 : sp);
   }
   const size_t tile_bytes = (size_t)d.BW * KC * sizeof(float);

@@ -6,14 +6,18 @@ import flex_b200 as fx
 from flex_b200 import synth
 from flex_b200.shard import panel_shards
 w, G, k = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 128
+fmt = sys.argv[4] if len(sys.argv) > 4 else "tcw"
+only_first = int(os.environ.get("ONLY_FIRST", "0"))
 rp, c, v = synth.generate(w, device="cuda")
 n, nnz = rp.numel() - 1, c.numel()
 dl = fx.DataLoader.from_device(n, nnz, rp.int().data_ptr(), c.int().data_ptr(), v.data_ptr(), k, w + ".csv")
 rph = rp.cpu().numpy()
 B = synth.dense_B(n, k, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
-for lo, hi in panel_shards(rph, G):
-    mat = fx.Mat(dl, fmt="aspt", row_begin=lo, row_end=hi)
+for si, (lo, hi) in enumerate(panel_shards(rph, G)):
+    if only_first and si >= only_first:
+        break
+    mat = fx.Mat(dl, fmt=fmt, row_begin=lo, row_end=hi)
     C = torch.empty((hi - lo, k), device="cuda")
     for _ in range(5):
         mat.spmm(B.data_ptr(), C.data_ptr(), k, stream=st)
@@ -23,6 +27,5 @@ for lo, hi in panel_shards(rph, G):
     for _ in range(20):
         mat.spmm(B.data_ptr(), C.data_ptr(), k, stream=st)
     e1.record(); e1.synchronize()
-    e = mat.export_aspt()
-    print(f"rows [{lo},{hi}) nnz={int(rph[hi]-rph[lo])} ms={e0.elapsed_time(e1)/20:.4f} special_chunks={int((np.diff(e['mcsr_e'])>=0).sum()*0)} tPre={mat.tPre_ms:.3f}", flush=True)
+    print(f"rows [{lo},{hi}) nnz={int(rph[hi]-rph[lo])} ms={e0.elapsed_time(e1)/20:.4f} tPre={mat.tPre_ms:.3f}", flush=True)
     mat.free()
