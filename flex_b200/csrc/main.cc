@@ -1,4 +1,4 @@
-// flexb200 <path.csv> <k> [--order ovo|deg|rcm|gor] [--format aspt|csr]
+// flexb200 <path.csv> <k> [--order ovo|deg|rcm|gor] [--format tcw|aspt|csr]
 // CLI mirror of `./flex <csv> <k>` (main.cu:7-13) and `./sspmm_128 <csv> <k>`
 // (aspt/sspmm_128.cu:1460-1468): loads the CSV, optionally reorders, builds the tile format on the
 // GPU, runs C = A*B with the reference's B stream, prints the reference's report lines.
@@ -9,20 +9,20 @@
 
 int main(int argc, char** argv) {
   if (argc < 3) {
-    std::fprintf(stderr, "usage: %s <path.csv> <k> [--order ovo|deg|rcm|gor] [--format aspt|csr]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s <path.csv> <k> [--order ovo|deg|rcm|gor] [--format tcw|aspt|csr]\n", argv[0]);
     return 2;
   }
   try {
     const int k = std::atoi(argv[2]);
     fx_order ord = FX_ORDER_OVO;
-    int fmt = FX_FMT_ASPT;
+    int fmt = FX_FMT_TCW;
     for (int i = 3; i + 1 < argc; i += 2) {
       if (!std::strcmp(argv[i], "--order")) {
         const char* o = argv[i + 1];
         ord = !std::strcmp(o, "deg") ? FX_ORDER_DEG : !std::strcmp(o, "rcm") ? FX_ORDER_RCM
               : !std::strcmp(o, "gor") ? FX_ORDER_GOR : FX_ORDER_OVO;
       } else if (!std::strcmp(argv[i], "--format")) {
-        fmt = !std::strcmp(argv[i + 1], "csr") ? FX_FMT_CSR : FX_FMT_ASPT;
+        fmt = !std::strcmp(argv[i + 1], "csr") ? FX_FMT_CSR : !std::strcmp(argv[i + 1], "aspt") ? FX_FMT_ASPT : FX_FMT_TCW;
       }
     }
     std::printf("-----------  %s  ---------------- start \n", argv[1]);

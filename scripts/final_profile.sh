@@ -10,7 +10,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu1.log 2>&1
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:^k_spmm -c 60 --csv \
   --log-file gpurun_out/dram_default.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_spmm_panel -s 2 -c 1 -o gpurun_out/panel_tcw_full -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_spmm_rows -s 2 -c 1 -o gpurun_out/rows_full -f \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu3.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_spmm_tc -s 2 -c 1 -o gpurun_out/tc_full -f \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu4.log 2>&1
