@@ -216,7 +216,8 @@ def workload_config(args, k, n, nnz):
             "k": k, "format": args.fmt, "order": args.order, "shuffled_ids": bool(args.shuffle),
             "l2_policy": "inputs larger than L2 (A+B+C bytes > 126 MB)" if algorithmic_bytes(n, nnz, k) > 126e6
             else "whole problem fits L2: L2 flushed by a 256 MB write between timed steps",
-            "arithmetic": ("fp32 FMA for the remainder; tensor windows on tcgen05 with the 3xTF32 split (hi*hi + hi*lo + lo*hi), "
+            "arithmetic": ("fp32 mul+add on the host cores (the reference's CPU SpMM)" if args.impl == "reference" else
+                           "fp32 FMA for the remainder; tensor windows on tcgen05 with the 3xTF32 split (hi*hi + hi*lo + lo*hi), "
                            "fp32 accumulate" if args.fmt == "tcw" else "fp32 FMA"),
             "parallelism": f"row-panel shards x{args.gpus}, B replicated"}
 
