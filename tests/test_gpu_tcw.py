@@ -119,3 +119,37 @@ def test_dense_panel(orc):
     res = run_spmm(mat, B, n)
     assert_close(orc, gold, res, rp)
     mat.free()
+
+
+@pytest.mark.parametrize("k", [5, 8, 36, 100, 132])
+def test_odd_feature_widths(orc, k):
+    """k not a multiple of 32: the last column block of the tensor kernel and of the row kernel is partial;
+    k not a multiple of 4 takes the raw CSR path (same as FX_FMT_ASPT)."""
+    n = 900
+    rp, c, v = random_csr(n, 8, 77, hubs=1, blocks=5)
+    dl = fx.DataLoader.from_arrays(rp, c, v, k)
+    B = rand_dense(n, k, 2)
+    gold = orc.spmm_ref(rp, c, v, B)
+    mat = fx.Mat(dl, fmt="tcw", tc_min_total=-1)
+    assert mat.tcw_info()["ntc"] > 0
+    res = run_spmm(mat, B, n)
+    assert_close(orc, gold, res, rp)
+    out = mat.spmm_host(B)
+    assert_close(orc, gold, out, rp)
+    mat.free()
+
+
+def test_tiles_in_the_remainder(orc, monkeypatch):
+    """The remainder goes through the ASpT builder: force its shared-memory tile path on as well."""
+    monkeypatch.setenv("FLEX_TILES", "1")
+    n, k = 1500, 128
+    rp, c, v = random_csr(n, 6, 21, hubs=2, blocks=8)
+    dl = fx.DataLoader.from_arrays(rp, c, v, k)
+    B = rand_dense(n, k, 3)
+    gold = orc.spmm_ref(rp, c, v, B)
+    # a narrow window leaves dense column blocks in the remainder
+    mat = fx.Mat(dl, fmt="tcw", tc_width=32, tc_min_total=-1, tc_min_gain=-1)
+    assert_plan_equal(mat, rp, c, v, W=32, min_gain=0, min_total=0)
+    res = run_spmm(mat, B, n)
+    assert_close(orc, gold, res, rp)
+    mat.free()
