@@ -13,6 +13,8 @@
 //     into a scratch buffer by a first kernel and folded in, in a fixed order, by the row's owner.
 #include <cooperative_groups.h>
 
+#include <type_traits>
+
 #include "fx_common.cuh"
 #include "fx_tc_kernel.cuh"
 
@@ -51,7 +53,48 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                : "memory");
 }
 
-__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+// L2 residency: the step touches B (re-read per nz, the only reused data) next to streams read or written once
+// (A's columns and values, tc_out, the chunk partials, C).  B rows are loaded with an evict_last policy, the
+// streams bypass L1 and carry evict_first, so B stays in L2 when the streams pass through (`hints` = 0 gives
+// every access the normal priority: FLEX_HINTS=0).
+struct Policies { uint64_t keep, stream; };
+__device__ __forceinline__ Policies make_policies(int hints) {
+  Policies p;
+  if (hints) {
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
+  } else {
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p.keep));
+    p.stream = p.keep;
+  }
+  return p;
+}
+__device__ __forceinline__ float4 ldg4_keep(const float4* p, uint64_t pol) {
+  float4 v;
+  asm("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float4 ldg4_stream(const float4* p, uint64_t pol) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int ldg_stream(const int* p, uint64_t pol) {
+  int v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ldg_stream(const float* p, uint64_t pol) {
+  float v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg4_stream(float4* p, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
 // acc += v * b with two packed FFMA2 (fma.rn.f32x2, sm_100+): same rounding as four fmaf, half the
 // issue slots -- the panel kernel is issue-bound, not FMA-bound.
 __device__ __forceinline__ void fma4(float4& a, float v, const float4& b) {
@@ -72,26 +115,27 @@ __device__ __forceinline__ void fma4(float4& a, float v, const float4& b) {
 template <int LPR, class Tile>
 __device__ __forceinline__ void accum_global(const Tile& tile, int lo, int hi, const int* __restrict__ ce,
                                              const float* __restrict__ cv, const float4* __restrict__ B4,
-                                             unsigned k4, float4& acc) {
+                                             unsigned k4, float4& acc, const Policies& pol) {
   const int sl = tile.thread_rank();
   for (int e0 = lo; e0 < hi; e0 += LPR) {
     const int e = e0 + sl;
     unsigned off = 0;
     float v = 0.f;
-    if (e < hi) { off = (unsigned)ce[e] * k4; v = cv[e]; }
+    if (e < hi) { off = (unsigned)ldg_stream(ce + e, pol.stream) * k4; v = ldg_stream(cv + e, pol.stream); }
     const int cnt = min(LPR, hi - e0);
     int j = 0;
     for (; j + 4 <= cnt; j += 4) {
       const unsigned o0 = tile.shfl(off, j), o1 = tile.shfl(off, j + 1), o2 = tile.shfl(off, j + 2),
                      o3 = tile.shfl(off, j + 3);
       const float v0 = tile.shfl(v, j), v1 = tile.shfl(v, j + 1), v2 = tile.shfl(v, j + 2), v3 = tile.shfl(v, j + 3);
-      const float4 b0 = ldg4(B4 + o0), b1 = ldg4(B4 + o1), b2 = ldg4(B4 + o2), b3 = ldg4(B4 + o3);
+      const float4 b0 = ldg4_keep(B4 + o0, pol.keep), b1 = ldg4_keep(B4 + o1, pol.keep), b2 = ldg4_keep(B4 + o2, pol.keep),
+                   b3 = ldg4_keep(B4 + o3, pol.keep);
       fma4(acc, v0, b0); fma4(acc, v1, b1); fma4(acc, v2, b2); fma4(acc, v3, b3);
     }
     for (; j < cnt; ++j) {
       const unsigned o = tile.shfl(off, j);
       const float vv = tile.shfl(v, j);
-      fma4(acc, vv, ldg4(B4 + o));
+      fma4(acc, vv, ldg4_keep(B4 + o, pol.keep));
     }
   }
 }
@@ -113,6 +157,7 @@ struct PanelArgs {
   // FX_FMT_TCW: products of the panels' tensor windows, added when a row is stored
   const float* tc_out;  // [ntc][128][k]
   const int* tc_slot;   // [npanel] position in tc_out or -1; nullptr = no windows
+  int hints;            // L2 eviction priorities (make_policies)
 };
 
 // ---- long-row chunks: partial[i,:] = sum over the i-th 512-nz chunk --------------------------
@@ -136,7 +181,8 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special(PanelArgs a, 
   const int nch = a.spec_off[row + 1] - a.spec_off[row];
   const int lo = a.mcsr_e[cnt0 * BH + (r + 1) * delta] - nch * STHRESHOLD + off;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  accum_global<LPR>(tile, lo, lo + STHRESHOLD, a.csr_e, a.csr_ev, reinterpret_cast<const float4*>(a.B) + c4, k4, acc);
+  const Policies pol = make_policies(a.hints);
+  accum_global<LPR>(tile, lo, lo + STHRESHOLD, a.csr_e, a.csr_ev, reinterpret_cast<const float4*>(a.B) + c4, k4, acc, pol);
   if (col_ok) reinterpret_cast<float4*>(partial)[(size_t)item * k4 + c4] = acc;
 }
 
@@ -162,7 +208,8 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special_cta(PanelArgs
   const int nch = a.spec_off[row + 1] - a.spec_off[row];
   const int lo = a.mcsr_e[cnt0 * BH + (r + 1) * delta] - nch * STHRESHOLD + off + wk * SLICE;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  accum_global<LPR>(tile, lo, lo + SLICE, a.csr_e, a.csr_ev, reinterpret_cast<const float4*>(a.B) + c4, k4, acc);
+  const Policies pol = make_policies(a.hints);
+  accum_global<LPR>(tile, lo, lo + SLICE, a.csr_e, a.csr_ev, reinterpret_cast<const float4*>(a.B) + c4, k4, acc, pol);
   reinterpret_cast<float4*>(red[wk])[sl] = acc;
   __syncthreads();
   if (wk == 0 && col_ok) {
@@ -190,13 +237,17 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special_cta(PanelArgs
 // TILES=false: no dynamic shared memory beyond the staging buffers, the SM keeps its L1.
 // TILES=true : the first TS dense tiles of the panel are TMA-staged in shared memory; nz of those
 //              tiles read B from there, all other nz (further tiles, sparse tail) from L1/L2.
-template <int KC, int WARPS, bool TILES, int MINB>
+// G = B rows requested back to back before the first FMA of a group (a multiple of 4, at most LPR): the loaded
+// rows sit in registers, so G*4 registers per thread are the kernel's in-flight buffer.  At 40 registers (three
+// 16-warp CTAs per SM) the compiler cannot hold more than four rows; G = 16 needs the 64-80 register launch
+// configurations (launch_aspt).
+template <int KC, int WARPS, bool TILES, int MINB, int G>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, const int* __restrict__ plist) {
   constexpr int LPR = KC / 4, RPW = 32 / LPR;  // NW = WARPS * RPW workers per CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // dynamic shared memory: [TILES: TS*BW*KC floats] [sbuf: NW*2*LPR uint2]
+  // dynamic shared memory: [TILES: TS*BW*KC floats] [sbuf: NW * 2 buffers * (LPR offsets + LPR values)]
   float* stile = reinterpret_cast<float*>(smem_raw);  // [TS][BW][KC]
-  uint2* sbuf = reinterpret_cast<uint2*>(reinterpret_cast<float*>(smem_raw) + (TILES ? (size_t)a.TS * a.BW * KC : 0));
+  uint32_t* sbuf = reinterpret_cast<uint32_t*>(reinterpret_cast<float*>(smem_raw) + (TILES ? (size_t)a.TS * a.BW * KC : 0));
   __shared__ int P[BH + 1], RS[BH];
   __shared__ int next_row, next_row2;
   __shared__ uint64_t bar;
@@ -280,15 +331,32 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
   if (TILES && ntres > 0) mbar_wait(&bar, 0);
 
   const float4* S4 = reinterpret_cast<const float4*>(stile) + sl;
+  const Policies pol = make_policies(a.hints);
   auto bload = [&](unsigned o) -> float4 {
     if (TILES && (o & 0x80000000u)) return S4[o & 0x7fffffffu];
-    return ldg4(B4 + o);
+    return ldg4_keep(B4 + o, pol.keep);
   };
-  uint2* sb0 = sbuf + (size_t)w * 2 * LPR;
+  uint32_t* sb0 = sbuf + (size_t)w * 4 * LPR;  // [2 buffers][offsets LPR | values LPR]
   int buf = 0;
+  // one group: M*4 B rows requested back to back, then their FMAs in nz order
+  auto group = [&](auto mtag, const uint32_t* so, float4& acc) {
+    constexpr int M = decltype(mtag)::value;
+    float4 b[4 * M];
+#pragma unroll
+    for (int q = 0; q < M; ++q) {
+      const uint4 o = *reinterpret_cast<const uint4*>(so + 4 * q);
+      b[4 * q] = bload(o.x); b[4 * q + 1] = bload(o.y); b[4 * q + 2] = bload(o.z); b[4 * q + 3] = bload(o.w);
+    }
+#pragma unroll
+    for (int q = 0; q < M; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(so + LPR + 4 * q);
+      fma4(acc, v.x, b[4 * q]); fma4(acc, v.y, b[4 * q + 1]); fma4(acc, v.z, b[4 * q + 2]); fma4(acc, v.w, b[4 * q + 3]);
+    }
+  };
   // two passes over the panel's rows, each through its own counter: the long rows first, so that no
   // worker starts one when the others are about to run out of rows
   constexpr int LONG_ROW = 96;
+  constexpr int GM = (G < LPR ? G : LPR) / 4;  // quads per full group
   int pass = 0;
   for (;;) {
     int r = 0;
@@ -305,10 +373,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = 0; i < L; i += LPR) {
       const int cnt = min(LPR, L - i);
-      // lanes past the end repeat the chunk's last nz with value 0: the tail group needs no branches
+      // lanes past the end repeat the chunk's last nz with value 0: every staged entry is a valid B row, and the
+      // tail group is padded to a multiple of four without branches
       const int e = rs + i + min(sl, cnt - 1);
-      const int c = a.csr_e[e];
-      const float v = sl < cnt ? a.csr_ev[e] : 0.f;
+      const int c = ldg_stream(a.csr_e + e, pol.stream);
+      const float v = sl < cnt ? ldg_stream(a.csr_ev + e, pol.stream) : 0.f;
       unsigned off = (unsigned)c * k4;
       if (TILES && ntres > 0) {
         const int base = cnt0 * BH + r * delta;
@@ -318,27 +387,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
           off = 0x80000000u | (unsigned)((g * BW + (c & (BW - 1))) * (KC / 4));
         }
       }
-      uint2* sb = sb0 + buf * LPR;
-      sb[sl] = make_uint2(off, __float_as_uint(v));
+      uint32_t* sb = sb0 + buf * 2 * LPR;
+      sb[sl] = off;
+      sb[LPR + sl] = __float_as_uint(v);
       tile.sync();
-      int j = 0;
-      if (LPR >= 8) {
-        for (; j + 8 <= cnt; j += 8) {
-          const uint4 t0 = *reinterpret_cast<const uint4*>(sb + j), t1 = *reinterpret_cast<const uint4*>(sb + j + 2),
-                      t2 = *reinterpret_cast<const uint4*>(sb + j + 4), t3 = *reinterpret_cast<const uint4*>(sb + j + 6);
-          const float4 b0 = bload(t0.x), b1 = bload(t0.z), b2 = bload(t1.x), b3 = bload(t1.z), b4 = bload(t2.x),
-                       b5 = bload(t2.z), b6 = bload(t3.x), b7 = bload(t3.z);
-          fma4(acc, __uint_as_float(t0.y), b0); fma4(acc, __uint_as_float(t0.w), b1);
-          fma4(acc, __uint_as_float(t1.y), b2); fma4(acc, __uint_as_float(t1.w), b3);
-          fma4(acc, __uint_as_float(t2.y), b4); fma4(acc, __uint_as_float(t2.w), b5);
-          fma4(acc, __uint_as_float(t3.y), b6); fma4(acc, __uint_as_float(t3.w), b7);
-        }
-      }
-      for (; j < cnt; j += 4) {  // up to 3 padded nz (value 0) in the last group
-        const uint4 t0 = *reinterpret_cast<const uint4*>(sb + j), t1 = *reinterpret_cast<const uint4*>(sb + j + 2);
-        const float4 b0 = bload(t0.x), b1 = bload(t0.z), b2 = bload(t1.x), b3 = bload(t1.z);
-        fma4(acc, __uint_as_float(t0.y), b0); fma4(acc, __uint_as_float(t0.w), b1);
-        fma4(acc, __uint_as_float(t1.y), b2); fma4(acc, __uint_as_float(t1.w), b3);
+      int q4 = (cnt + 3) >> 2;  // quads of this chunk, the last one padded
+      const uint32_t* so = sb;
+      for (; q4 >= GM; q4 -= GM, so += 4 * GM) group(std::integral_constant<int, GM>{}, so, acc);
+      if (GM > 1) {
+        if (GM > 2 && q4 >= 3) group(std::integral_constant<int, (GM > 2 ? 3 : 1)>{}, so, acc);
+        else if (q4 == 2) group(std::integral_constant<int, 2>{}, so, acc);
+        else if (q4 == 1) group(std::integral_constant<int, 1>{}, so, acc);
       }
       buf ^= 1;
     }
@@ -348,18 +407,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
       const int so = a.spec_off[row], nch = a.spec_off[row + 1] - so;
       const float4* P4 = reinterpret_cast<const float4*>(a.partial) + (size_t)so * k4 + c4;
       for (int c = 0; c < nch; ++c) {
-        const float4 pp = P4[(size_t)c * k4];
+        const float4 pp = ldg4_stream(P4 + (size_t)c * k4, pol.stream);
         acc.x += pp.x; acc.y += pp.y; acc.z += pp.z; acc.w += pp.w;
       }
     }
     if (a.tc_slot) {
       const int ts = a.tc_slot[p];
       if (ts >= 0) {
-        const float4 tt = ldg4(reinterpret_cast<const float4*>(a.tc_out) + ((size_t)ts * BH + r) * k4 + c4);
+        const float4 tt = ldg4_stream(reinterpret_cast<const float4*>(a.tc_out) + ((size_t)ts * BH + r) * k4 + c4, pol.stream);
         acc.x += tt.x; acc.y += tt.y; acc.z += tt.z; acc.w += tt.w;
       }
     }
-    if (col_ok && row < a.nloc) C4[(size_t)row * k4] = acc;
+    if (col_ok && row < a.nloc) stg4_stream(C4 + (size_t)row * k4, acc, pol.stream);
   }
 }
 
@@ -376,8 +435,9 @@ __global__ void __launch_bounds__(256) k_spmm_csr_vec(const uint32_t* __restrict
   if (row >= nrows) return;
   const bool col_ok = c4 < (int)k4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const Policies pol = make_policies(1);
   accum_global<LPR>(tile, (int)rowptr[row], (int)rowptr[row + 1], reinterpret_cast<const int*>(col), val,
-                    reinterpret_cast<const float4*>(B) + (col_ok ? c4 : 0), k4, acc);
+                    reinterpret_cast<const float4*>(B) + (col_ok ? c4 : 0), k4, acc, pol);
   if (col_ok) reinterpret_cast<float4*>(C)[(size_t)row * k4 + c4] = acc;
 }
 
@@ -447,36 +507,37 @@ int spmm_csr(const uint32_t* rowptr, const uint32_t* col, const float* val, int6
   return FX_OK;
 }
 
-static int panel_warps() {
-  static int w = 0;
-  if (!w) {
-    const char* e = getenv("FLEX_PANEL_WARPS");
-    w = e ? atoi(e) : 16;
-    if (w != 8 && w != 16 && w != 24 && w != 32) w = 16;
+// Launch configurations of the row kernel: (warps per CTA, CTAs per SM the register cap is set for, rows in flight per group)
+static int rows_cfg() {
+  static int c = -1;
+  if (c < 0) {
+    const char* e = getenv("FLEX_ROWS_CFG");
+    c = e ? atoi(e) : 0;
+    if (c < 0 || c > 3) c = 0;
   }
-  return w;
+  return c;
 }
 
-template <int KC, int WARPS, int MINB, bool TILES>
+template <int KC, int WARPS, int MINB, int G, bool TILES>
 static int launch_one(PanelArgs a, const int* plist, int npan, const int2* wl, int nwl, int kchunks, size_t tile_smem,
                       cudaStream_t s) {
   constexpr int NW = WARPS * (32 / (KC / 4));
-  const size_t smem = tile_smem + (size_t)NW * 2 * (KC / 4) * sizeof(uint2);  // + per-worker (offset,value) staging
+  const size_t smem = tile_smem + (size_t)NW * 4 * (KC / 4) * sizeof(uint32_t);  // + per-worker offset / value staging
   static const bool no_wl = getenv("FLEX_NO_WORKLIST") != nullptr;
   // a uniform split (few panels, or FLEX_SPLIT) keeps the blockIdx mapping; otherwise the build's work list
   a.wl = (a.split == 1 && wl && nwl > 0 && !no_wl) ? wl : nullptr;
   dim3 grid(a.wl ? nwl : npan * a.split, kchunks);
   static size_t set = 0;
   if (smem > 48 * 1024 && smem > set) {
-    FX_CUDA(cudaFuncSetAttribute(k_spmm_rows<KC, WARPS, TILES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FX_CUDA(cudaFuncSetAttribute(k_spmm_rows<KC, WARPS, TILES, MINB, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     set = smem;
   }
-  k_spmm_rows<KC, WARPS, TILES, MINB><<<grid, WARPS * 32, smem, s>>>(a, plist);
+  k_spmm_rows<KC, WARPS, TILES, MINB, G><<<grid, WARPS * 32, smem, s>>>(a, plist);
   FX_LAUNCH_CHECK();
   return FX_OK;
 }
 
-template <int KC, int WARPS, int MINB>
+template <int KC, int WARPS, int MINB, int G>
 static int launch_panels(const fx_aspt_dev& d, const PanelArgs& a, int kchunks, cudaStream_t s) {
   // Shared-memory staging of dense tiles only pays when a large share of the nz sits in them: the
   // tile memory (64 KB per tile at k=128) comes out of the SM's L1, which serves the sparse nz.
@@ -485,13 +546,13 @@ static int launch_panels(const fx_aspt_dev& d, const PanelArgs& a, int kchunks, 
   const double dense_frac = d.ne > 0 ? (double)(d.ne - d.S1) / d.ne : 0.0;
   const bool use_tiles = tiles_env ? atoi(tiles_env) != 0 : dense_frac >= 0.25;
   if (!use_tiles || d.n_tiled == 0)  // every panel through the L1 path (dense groups are ordinary nz there)
-    return launch_one<KC, WARPS, MINB, false>(a, nullptr, d.npanel, d.wl_all, d.n_wl_all, kchunks, 0, s);
+    return launch_one<KC, WARPS, MINB, G, false>(a, nullptr, d.npanel, d.wl_all, d.n_wl_all, kchunks, 0, s);
   if (d.n_plain > 0) {
-    const int rc = launch_one<KC, WARPS, MINB, false>(a, d.n_tiled ? d.plist_plain : nullptr, d.n_plain, d.wl_plain, d.n_wl_plain, kchunks, 0, s);
+    const int rc = launch_one<KC, WARPS, MINB, G, false>(a, d.n_tiled ? d.plist_plain : nullptr, d.n_plain, d.wl_plain, d.n_wl_plain, kchunks, 0, s);
     if (rc != FX_OK) return rc;
   }
   if (d.n_tiled > 0)
-    return launch_one<KC, WARPS, MINB, true>(a, d.plist_tiled, d.n_tiled, d.wl_tiled, d.n_wl_tiled, kchunks, (size_t)a.TS * a.BW * KC * sizeof(float), s);
+    return launch_one<KC, WARPS, MINB, G, true>(a, d.plist_tiled, d.n_tiled, d.wl_tiled, d.n_wl_tiled, kchunks, (size_t)a.TS * a.BW * KC * sizeof(float), s);
   return FX_OK;
 }
 
@@ -511,12 +572,14 @@ static int launch_aspt(const fx_tiles* t, const PanelArgs& a, int special_p, cud
     }
     FX_LAUNCH_CHECK();
   }
-  static int minb = getenv("FLEX_MINB") ? atoi(getenv("FLEX_MINB")) : 3;
-  switch (panel_warps()) {
-    case 8: return minb >= 6 ? launch_panels<KC, 8, 6>(d, a, kchunks, s) : launch_panels<KC, 8, 1>(d, a, kchunks, s);
-    case 32: return launch_panels<KC, 32, 1>(d, a, kchunks, s);
-    case 24: return launch_panels<KC, 24, 2>(d, a, kchunks, s);
-    default: return minb >= 4 ? launch_panels<KC, 16, 4>(d, a, kchunks, s) : (minb >= 3 ? launch_panels<KC, 16, 3>(d, a, kchunks, s) : launch_panels<KC, 16, 1>(d, a, kchunks, s));
+  // Measured on Reddit-shape k=128 (ms per SpMM): 0.569 default; 0.576 <16,2,16>; 0.577 <16,2,8>; 0.582 <8,6,8>; fewer, fatter
+  // warps lose (<8,4,16> 0.589, <8,3,12> 0.617, <8,3,16> 0.631, <8,2,16> at 101 registers 0.689): the per-row latency chain
+  // (grab, metadata, B rounds, window product, store) is covered by warps, not by loads in flight per warp
+  switch (rows_cfg()) {
+    case 1: return launch_panels<KC, 16, 2, 16>(d, a, kchunks, s);  // 64 registers, 32 warps per SM
+    case 2: return launch_panels<KC, 16, 2, 8>(d, a, kchunks, s);
+    case 3: return launch_panels<KC, 8, 6, 8>(d, a, kchunks, s);    // 40 registers, 48 warps per SM in small CTAs
+    default: return launch_panels<KC, 16, 3, 8>(d, a, kchunks, s);  // 40 registers, 48 warps per SM
   }
 }
 
@@ -541,6 +604,8 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   const int KC = pick_kc(width);
   PanelArgs a;
   a.tc_out = nullptr; a.tc_slot = nullptr; a.wl = nullptr;
+  static const int hints = getenv("FLEX_HINTS") ? atoi(getenv("FLEX_HINTS")) : 1;
+  a.hints = hints;
   if (t->format == FX_FMT_TCW && t->tcw.ntc > 0) {  // tensor windows first; the panel kernel adds them in
     const fx_tcw_dev& w = t->tcw;
     fxtc::TcArgs ta;
