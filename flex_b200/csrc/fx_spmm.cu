@@ -75,6 +75,14 @@ __device__ __forceinline__ float4 ldg4_keep(const float4* p, uint64_t pol) {
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
   return v;
 }
+// B row `off` (in float4 units, < 2^32: fx_spmm refuses larger n*k) from this lane's base pointer: one IMAD.WIDE.U32 per
+// address (written as C++ pointer arithmetic the compiler re-derives the base from its parts and spends four
+// instructions per load on the 64-bit sum)
+__device__ __forceinline__ float4 ldg4_keep_at(const float4* base, unsigned off, uint64_t pol) {
+  const float4* p;
+  asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(p) : "r"(off), "l"(base));
+  return ldg4_keep(p, pol);
+}
 __device__ __forceinline__ float4 ldg4_stream(const float4* p, uint64_t pol) {
   float4 v;
   asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
@@ -128,14 +136,14 @@ __device__ __forceinline__ void accum_global(const Tile& tile, int lo, int hi, c
       const unsigned o0 = tile.shfl(off, j), o1 = tile.shfl(off, j + 1), o2 = tile.shfl(off, j + 2),
                      o3 = tile.shfl(off, j + 3);
       const float v0 = tile.shfl(v, j), v1 = tile.shfl(v, j + 1), v2 = tile.shfl(v, j + 2), v3 = tile.shfl(v, j + 3);
-      const float4 b0 = ldg4_keep(B4 + o0, pol.keep), b1 = ldg4_keep(B4 + o1, pol.keep), b2 = ldg4_keep(B4 + o2, pol.keep),
-                   b3 = ldg4_keep(B4 + o3, pol.keep);
+      const float4 b0 = ldg4_keep_at(B4, o0, pol.keep), b1 = ldg4_keep_at(B4, o1, pol.keep), b2 = ldg4_keep_at(B4, o2, pol.keep),
+                   b3 = ldg4_keep_at(B4, o3, pol.keep);
       fma4(acc, v0, b0); fma4(acc, v1, b1); fma4(acc, v2, b2); fma4(acc, v3, b3);
     }
     for (; j < cnt; ++j) {
       const unsigned o = tile.shfl(off, j);
       const float vv = tile.shfl(v, j);
-      fma4(acc, vv, ldg4_keep(B4 + o, pol.keep));
+      fma4(acc, vv, ldg4_keep_at(B4, o, pol.keep));
     }
   }
 }
@@ -189,6 +197,8 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special(PanelArgs a, 
 // Few chunks (small matrices with a handful of long rows): one CTA per chunk, its workers take equal
 // slices of the 512 nz and are summed in worker order through shared memory, so that a short list of
 // chunks still fills the machine (one warp streaming 512 nz alone is pure DRAM latency).
+// (tried: metadata staged in shared memory and read with broadcast LDS.128 as in k_spmm_rows instead of two SHFL per nz --
+// the shuffles are 29 % of this kernel's L1 data-pipe wavefronts -- same time: 0.5676 vs 0.5669 ms on Reddit-shape k=128)
 template <int KC>
 __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special_cta(PanelArgs a, const int* __restrict__ special,
                                                                       const int* __restrict__ special2,
@@ -274,6 +284,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
   const float4* B4 = reinterpret_cast<const float4*>(a.B) + c4;
   float4* C4 = reinterpret_cast<float4*>(a.C) + c4;
   const int BW = a.BW;
+  const int tslot = a.tc_slot ? a.tc_slot[p] : -1;  // position of the panel's tensor-window product, -1 = none
 
   if (TILES && ntres > 0) {
     if (threadIdx.x == 0) {
@@ -334,7 +345,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
   const Policies pol = make_policies(a.hints);
   auto bload = [&](unsigned o) -> float4 {
     if (TILES && (o & 0x80000000u)) return S4[o & 0x7fffffffu];
-    return ldg4_keep(B4 + o, pol.keep);
+    return ldg4_keep_at(B4, o, pol.keep);
   };
   uint32_t* sb0 = sbuf + (size_t)w * 4 * LPR;  // [2 buffers][offsets LPR | values LPR]
   int buf = 0;
@@ -358,28 +369,42 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
   constexpr int LONG_ROW = 96;
   constexpr int GM = (G < LPR ? G : LPR) / 4;  // quads per full group
   int pass = 0;
-  for (;;) {
-    int r = 0;
-    if (sl == 0) r = atomicAdd(pass == 0 ? &next_row : &next_row2, 1);
-    r = tile.shfl(r, 0);
-    if (r >= rhi) {
-      if (pass == 1) break;
-      pass = 1;
-      continue;
+  auto grab = [&](int& Lr) -> int {  // next row of this pass (its handled length in Lr), -1 when the panel is done
+    for (;;) {
+      int r = 0;
+      if (sl == 0) r = atomicAdd(pass == 0 ? &next_row : &next_row2, 1);
+      r = tile.shfl(r, 0);
+      if (r >= rhi) {
+        if (pass == 1) return -1;
+        pass = 1;
+        continue;
+      }
+      Lr = split > 1 ? P[r + 1] - P[r] : P[r + 1];
+      if ((Lr >= LONG_ROW) == (pass == 0)) return r;
     }
-    const int rs = RS[r];
-    const int L = split > 1 ? P[r + 1] - P[r] : P[r + 1];
-    if ((L >= LONG_ROW) != (pass == 0)) continue;
+  };
+  // (column, value) of this lane's nz in the row's chunk at i; lanes past the end repeat the chunk's last nz (masked to
+  // value 0 when staged): every staged entry is a valid B row and the tail group is padded without branches
+  auto meta = [&](int rr, int LL, int i, int& cc, float& vv) {
+    const int e = RS[rr] + i + min(sl, min(LPR, LL - i) - 1);
+    cc = ldg_stream(a.csr_e + e, pol.stream);
+    vv = ldg_stream(a.csr_ev + e, pol.stream);
+  };
+  int L = 0, c = 0;
+  float v = 0.f;
+  // (tried: taking the next row and requesting its first metadata before this row's B requests go out -- 0.597 vs
+  // 0.564 ms on Reddit-shape k=128 at the same 40 registers; rows of different workers already overlap)
+  for (int r = grab(L); r >= 0; r = grab(L)) {
+    // the accumulator starts from the row's tensor-window product (requested here, needed by the first FMA: its
+    // latency runs under the metadata and B requests instead of ending the row)
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tslot >= 0) acc = ldg4_stream(reinterpret_cast<const float4*>(a.tc_out) + ((size_t)tslot * BH + r) * k4 + c4, pol.stream);
     for (int i = 0; i < L; i += LPR) {
       const int cnt = min(LPR, L - i);
-      // lanes past the end repeat the chunk's last nz with value 0: every staged entry is a valid B row, and the
-      // tail group is padded to a multiple of four without branches
-      const int e = rs + i + min(sl, cnt - 1);
-      const int c = ldg_stream(a.csr_e + e, pol.stream);
-      const float v = sl < cnt ? ldg_stream(a.csr_ev + e, pol.stream) : 0.f;
+      meta(r, L, i, c, v);
       unsigned off = (unsigned)c * k4;
       if (TILES && ntres > 0) {
+        const int e = RS[r] + i + min(sl, cnt - 1);
         const int base = cnt0 * BH + r * delta;
         if (e < a.mcsr_e[base + ntres]) {
           int g = 0;
@@ -389,7 +414,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
       }
       uint32_t* sb = sb0 + buf * 2 * LPR;
       sb[sl] = off;
-      sb[LPR + sl] = __float_as_uint(v);
+      sb[LPR + sl] = sl < cnt ? __float_as_uint(v) : 0u;
       tile.sync();
       int q4 = (cnt + 3) >> 2;  // quads of this chunk, the last one padded
       const uint32_t* so = sb;
@@ -401,7 +426,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
       }
       buf ^= 1;
     }
-    // add the row's 512-chunk partials (chunk order) and its tensor-window product, store once
+    // add the row's 512-chunk partials (chunk order), store once
     const int row = p * BH + r;
     if (a.spec_off) {
       const int so = a.spec_off[row], nch = a.spec_off[row + 1] - so;
@@ -409,13 +434,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
       for (int c = 0; c < nch; ++c) {
         const float4 pp = ldg4_stream(P4 + (size_t)c * k4, pol.stream);
         acc.x += pp.x; acc.y += pp.y; acc.z += pp.z; acc.w += pp.w;
-      }
-    }
-    if (a.tc_slot) {
-      const int ts = a.tc_slot[p];
-      if (ts >= 0) {
-        const float4 tt = ldg4_stream(reinterpret_cast<const float4*>(a.tc_out) + ((size_t)ts * BH + r) * k4 + c4, pol.stream);
-        acc.x += tt.x; acc.y += tt.y; acc.z += tt.z; acc.w += tt.w;
       }
     }
     if (col_ok && row < a.nloc) stg4_stream(C4 + (size_t)row * k4, acc, pol.stream);
