@@ -16,6 +16,7 @@
 #include <cooperative_groups/scan.h>
 
 #include "fx_common.cuh"
+#include "fx_scan.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -406,30 +407,7 @@ __global__ void k_nodense(const int* __restrict__ csr_v, int npanel, int nr, int
 // ---- K5: special lists (make_special :1076-1087) in canonical (row-ascending) order ---------
 __global__ void __launch_bounds__(1024) k_scan_spec(const int* __restrict__ spec_cnt, int nr,
                                                     int* __restrict__ spec_off) {
-  __shared__ int warp_sum[32];
-  __shared__ int carry_s;
-  auto warp = cg::tiled_partition<32>(cg::this_thread_block());
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < nr; base += blockDim.x) {
-    int i = base + threadIdx.x;
-    int v = i < nr ? spec_cnt[i] : 0;
-    int inc = cg::inclusive_scan(warp, v);
-    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = inc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int ws = warp_sum[threadIdx.x];
-      int wi = cg::inclusive_scan(warp, ws);
-      warp_sum[threadIdx.x] = wi - ws;
-    }
-    __syncthreads();
-    int incl = carry_s + warp_sum[threadIdx.x >> 5] + inc;
-    if (i < nr) spec_off[i] = incl - v;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry_s = incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) spec_off[nr] = carry_s;
+  fx::cta_exclusive_scan(spec_cnt, nr, spec_off);
 }
 
 __global__ void k_fill_special(const int* __restrict__ spec_cnt, const int* __restrict__ spec_off, int nr,

@@ -30,6 +30,7 @@
 #include <algorithm>
 
 #include "fx_common.cuh"
+#include "fx_scan.cuh"
 #include "fx_tc_kernel.cuh"
 
 namespace cg = cooperative_groups;
@@ -199,30 +200,7 @@ __global__ void k_tcw_gate(const unsigned long long* __restrict__ stats, long lo
 
 // exclusive scan by one CTA: out[n] = total
 __global__ void __launch_bounds__(1024) k_tcw_scan(const int* __restrict__ in, int n, int* __restrict__ out) {
-  __shared__ int warp_sum[32];
-  __shared__ int carry_s;
-  auto warp = cg::tiled_partition<32>(cg::this_thread_block());
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += blockDim.x) {
-    const int i = base + threadIdx.x;
-    const int v = i < n ? in[i] : 0;
-    const int inc = cg::inclusive_scan(warp, v);
-    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = inc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      const int ws = warp_sum[threadIdx.x];
-      const int wi = cg::inclusive_scan(warp, ws);
-      warp_sum[threadIdx.x] = wi - ws;
-    }
-    __syncthreads();
-    const int incl = carry_s + warp_sum[threadIdx.x >> 5] + inc;
-    if (i < n) out[i] = incl - v;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry_s = incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) out[n] = carry_s;
+  fx::cta_exclusive_scan(in, n, out);
 }
 
 __global__ void k_tcw_rowptr(const int* __restrict__ csr_v, const int* __restrict__ win_rowptr, int nloc,
