@@ -66,20 +66,21 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       : "memory");
 }
 
+// round to nearest (ties away) tf32 = cvt.rna.tf32.f32 for finite x, done on the bit pattern: the cvt instruction is
+// emulated on sm_100a (VIADD 0x1000, an Inf/NaN test, SEL, LOP3 -- four instructions per value, and a chunk converts
+// 16 B values + its nz per thread twice: 42 % of the kernel's instructions were this conversion)
 __device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "TC_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"  // suspend-time hint: the spin was 11 % of the kernel's instructions
       "@p bra TC_DONE;\n\t"
       "bra TC_WAIT;\n\t"
-      "TC_DONE:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+      "TC_DONE:\n\t}" ::"r"(smem_addr(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 
 // 4-byte word of element (r, kk) in a K-major 128 x 32 tile with LBO = 128, SBO = 1024 bytes: the builder
@@ -90,6 +91,9 @@ __host__ __device__ __forceinline__ uint32_t tile_word(int r, int kk) {
 
 // grid = (ntc, ceil(k / N)), block = 256.  Dynamic shared memory: 2*128*32*4 + 2*N*32*4 + 4*W bytes, so three
 // CTAs share an SM and the staging of one overlaps the MMAs of another.
+// (tried: leaving the low part unrounded -- the tensor core reads its upper 19 bits -- for two instructions less per value:
+// same time, so the rounding stays.  The kernel is bound by its per-chunk chain of barriers, fence and MMA wait, not by
+// instruction issue: dropping 17 % of its instructions moved the step by 0.3 %.)
 template <int N>
 __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
   constexpr int TM_COLS = N < 32 ? 32 : N;
