@@ -241,7 +241,7 @@ constexpr int WL_MAX_PARTS = 16;
 __global__ void __launch_bounds__(1024) k_worklist(const int* __restrict__ plist, int mode, const int* __restrict__ csr_v,
                                                    const int* __restrict__ spec_off, int nr, int npanel_all,
                                                    int2* __restrict__ wl, int cap, const unsigned long long* __restrict__ stats,
-                                                   unsigned long long* __restrict__ count) {
+                                                   unsigned long long* __restrict__ count, int nclass) {
   __shared__ int warp_sum[32];
   __shared__ int carry_s;
   auto warp = cg::tiled_partition<32>(cg::this_thread_block());
@@ -253,6 +253,9 @@ __global__ void __launch_bounds__(1024) k_worklist(const int* __restrict__ plist
   const long long handled_all = (long long)csr_v[nr] - (long long)STHRESHOLD * spec_off[nr];
   const long long mean = handled_all / (npanel_all > 0 ? npanel_all : 1);
   const long long target = mean * 2 > 4096 ? mean * 2 : 4096;
+  // nclass > 1: the list is emitted heaviest class first (work per entry >= 1.5, 1, 0.5 times the mean panel, the rest;
+  // panel order inside a class), so that the grid ends on short CTAs instead of on whatever the last panels hold
+  for (int cls = 0; cls < nclass; ++cls)
   for (int base = 0; base < npan; base += blockDim.x) {
     const int i = base + threadIdx.x;
     int parts = 0, p = 0;
@@ -262,6 +265,11 @@ __global__ void __launch_bounds__(1024) k_worklist(const int* __restrict__ plist
                           (long long)STHRESHOLD * (spec_off[(p + 1) * BH] - spec_off[p * BH]);
       parts = (int)((h + target - 1) / target);
       parts = parts < 1 ? 1 : (parts > WL_MAX_PARTS ? WL_MAX_PARTS : parts);
+      if (nclass > 1) {
+        const long long w2 = 2 * h / parts;  // twice the work of one entry
+        const int c = w2 >= 3 * mean ? 0 : (w2 >= 2 * mean ? 1 : (w2 >= mean ? 2 : 3));
+        if ((c < nclass ? c : nclass - 1) != cls) parts = 0;
+      }
     }
     const int inc = cg::inclusive_scan(warp, parts);
     if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = inc;
@@ -549,12 +557,17 @@ int aspt_build(fx_tiles* t, cudaStream_t s) {
   FX_LAUNCH_CHECK();
   k_fill_special<<<ceil_div(a.nr, 256), 256, 0, s>>>(a.spec_cnt, a.spec_off, a.nr, a.special, a.special2);
   FX_LAUNCH_CHECK();
-  k_worklist<<<1, 1024, 0, s>>>(nullptr, 0, a.csr_v, a.spec_off, a.nr, a.npanel, a.wl_all, a.wl_cap, a.stats, a.stats + 8);
+  // Heaviest entries first only when the grid is a few waves long (a.G = 2 CTAs per SM, the row kernel runs 3): there the
+  // tail is what counts (flickr-shape, 698 panels: 0.087 -> 0.073 ms); on long grids the panel order is worth more, because
+  // neighbouring panels share B rows in L2 (yelp-shape 0.576 -> 0.593 ms, Amazon-shape 6.55 -> 7.34 ms; Reddit-shape equal)
+  static const int wl_env = getenv("FLEX_WL_CLASSES") ? std::max(1, std::min(4, atoi(getenv("FLEX_WL_CLASSES")))) : 0;
+  const int wl_classes = wl_env ? wl_env : (a.npanel <= 3 * heavy_ctas(1 << 30) ? 4 : 1);
+  k_worklist<<<1, 1024, 0, s>>>(nullptr, 0, a.csr_v, a.spec_off, a.nr, a.npanel, a.wl_all, a.wl_cap, a.stats, a.stats + 8, wl_classes);
   FX_LAUNCH_CHECK();
   if (a.any_flag) {  // the tiled launch and the plain launch walk their own panel lists (counts are on the device)
-    k_worklist<<<1, 1024, 0, s>>>(a.plist_plain, 1, a.csr_v, a.spec_off, a.nr, a.npanel, a.wl_plain, a.wl_cap, a.stats, a.stats + 9);
+    k_worklist<<<1, 1024, 0, s>>>(a.plist_plain, 1, a.csr_v, a.spec_off, a.nr, a.npanel, a.wl_plain, a.wl_cap, a.stats, a.stats + 9, wl_classes);
     FX_LAUNCH_CHECK();
-    k_worklist<<<1, 1024, 0, s>>>(a.plist_tiled, 2, a.csr_v, a.spec_off, a.nr, a.npanel, a.wl_tiled, a.wl_cap, a.stats, a.stats + 10);
+    k_worklist<<<1, 1024, 0, s>>>(a.plist_tiled, 2, a.csr_v, a.spec_off, a.nr, a.npanel, a.wl_tiled, a.wl_cap, a.stats, a.stats + 10, wl_classes);
     FX_LAUNCH_CHECK();
   }
   FX_CUDA(cudaMemcpyAsync(t->stats_host, a.stats, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, s));
