@@ -61,6 +61,8 @@ struct Policies { uint64_t keep, stream; };
 __device__ __forceinline__ Policies make_policies(int hints) {
   Policies p;
   if (hints) {
+    // (tried: evict_last on a fixed fraction of B only, evict_first on the rest -- 0.75 / 0.5 / 0.25 are each worse than the
+    // one before: Reddit-shape 0.556 -> 0.573 / 0.593 / 0.621 ms, yelp-shape 0.583 -> 0.631 / 0.678 / 0.719)
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
   } else {
@@ -630,6 +632,7 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
     ta.win_cptr = w.win_cptr; ta.win_code = w.win_code; ta.win_val = w.win_val;
     ta.tc_panels = w.tc_panels; ta.tc_cols = w.tc_cols; ta.tc_ncol = w.tc_ncol;
     ta.B = B; ta.out = w.tc_out; ta.k = k; ta.width = width; ta.W = w.W;
+    ta.hints = getenv("FLEX_TC_HINTS") ? atoi(getenv("FLEX_TC_HINTS")) : hints;
     const int rc = KC == 32 ? launch_tc<32>(ta, w.ntc, s) : (KC == 64 ? launch_tc<64>(ta, w.ntc, s) : launch_tc<128>(ta, w.ntc, s));
     if (rc != FX_OK) return rc;
     a.tc_out = w.tc_out; a.tc_slot = w.tc_slot;

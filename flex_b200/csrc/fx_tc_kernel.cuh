@@ -39,6 +39,7 @@ struct TcArgs {
   float* out;                // [ntc][128][k]
   int k, W;   // k = row stride of B and out (floats)
   int width;  // feature columns computed, from the B/out pointers on
+  int hints;  // L2 eviction priorities on (FLEX_HINTS)
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -134,6 +135,20 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
 
   uint32_t phase = 0;
   const int nchunk = (ncol + TC_KCH - 1) / TC_KCH;
+  // L2 priorities as in the row kernel: B rows evict_last, the window's nz stream and the product evict_first
+  uint64_t pol_keep, pol_stream;
+  if (a.hints) {
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  } else {
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+    pol_stream = pol_keep;
+  }
+  auto ldB = [&](const float4* p) {
+    float4 v;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol_keep));
+    return v;
+  };
 
   // Software pipeline: the global loads of chunk ch+1 (B rows through the column list, the first nz
   // of every thread) are issued into registers before the MMAs of chunk ch, so their L2 latency runs
@@ -157,10 +172,10 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
     if (tid < UNITS) {
       const int4 gc = *reinterpret_cast<const int4*>(scols + ch * TC_KCH + kq * 4);
       if (unit_ok) {
-        if (gc.x >= 0) bx[0] = __ldg(Bq + (size_t)gc.x * k4);
-        if (gc.y >= 0) bx[1] = __ldg(Bq + (size_t)gc.y * k4);
-        if (gc.z >= 0) bx[2] = __ldg(Bq + (size_t)gc.z * k4);
-        if (gc.w >= 0) bx[3] = __ldg(Bq + (size_t)gc.w * k4);
+        if (gc.x >= 0) bx[0] = ldB(Bq + (size_t)gc.x * k4);
+        if (gc.y >= 0) bx[1] = ldB(Bq + (size_t)gc.y * k4);
+        if (gc.z >= 0) bx[2] = ldB(Bq + (size_t)gc.z * k4);
+        if (gc.w >= 0) bx[3] = ldB(Bq + (size_t)gc.w * k4);
       }
     }
 #pragma unroll
@@ -272,8 +287,8 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           if (n0 + c0 + j < a.width)
-            *reinterpret_cast<float4*>(dst + c0 + j) =
-                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(dst + c0 + j), "r"(v[j]),
+                         "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3]), "l"(pol_stream) : "memory");
       }
     }
   }
