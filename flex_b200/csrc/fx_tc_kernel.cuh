@@ -260,19 +260,25 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
     }
   }
 
-  // epilogue: TMEM lane = panel row; warp w reads lanes 32(w%4).., warps 0-3 the lower half of the
-  // features and warps 4-7 the upper half
+  // epilogue: TMEM lane = panel row; warp w reads lanes 32(w%4).., warps 0-3 the lower half of the features and warps
+  // 4-7 the upper half.  tcgen05.ld hands a thread 32 consecutive features of ITS row, so storing from there writes 16
+  // bytes to 32 different rows per instruction (32 L1 wavefronts; the epilogue was ~30 % of the kernel's L1 data-pipe
+  // time).  Each warp instead turns its 32 x 32 block through a padded slab of the (now idle) operand memory and stores
+  // four whole 128-byte row pieces per instruction.
   {
-    const int r = (warp & 3) * 32 + lane;
-    float* dst = a.out + ((size_t)slot * TC_BH + r) * a.k + n0;
     constexpr int HALF = N >= 64 ? N / 2 : N;
     const int cbeg = (N >= 64 && warp >= 4) ? HALF : 0;
     const bool active = N >= 64 || warp < 4;
+    constexpr int SLAB_STRIDE = 36;  // floats per staged row: 16-byte aligned, rows 4 banks apart
+    float* slab = reinterpret_cast<float*>(tc_smem) + warp * (32 * SLAB_STRIDE);
+    __syncthreads();  // every thread is past the last MMA wait: the operand tiles are free
     if (active) {
+      const int r0 = (warp & 3) * 32;
+      float* dst0 = a.out + ((size_t)slot * TC_BH + r0) * a.k + n0;
 #pragma unroll 1
       for (int c0 = cbeg; c0 < cbeg + HALF; c0 += 32) {
         uint32_t v[32];
-        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
+        const uint32_t taddr = tmem + ((uint32_t)r0 << 16) + (uint32_t)c0;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -286,9 +292,18 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          if (n0 + c0 + j < a.width)
-            asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(dst + c0 + j), "r"(v[j]),
-                         "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3]), "l"(pol_stream) : "memory");
+          *reinterpret_cast<uint4*>(slab + lane * SLAB_STRIDE + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        const int col = c0 + (lane & 7) * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3);
+          const uint4 x = *reinterpret_cast<const uint4*>(slab + rr * SLAB_STRIDE + (lane & 7) * 4);
+          if (n0 + col < a.width)
+            asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(dst0 + (size_t)rr * a.k + col),
+                         "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w), "l"(pol_stream) : "memory");
+        }
+        __syncwarp();  // the slab is rewritten by the next 32 features
       }
     }
   }

@@ -15,3 +15,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sp
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_spmm_tc -s 2 -c 1 -o gpurun_out/tc_full -f \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu4.log 2>&1
 ls -la gpurun_out | tail -12
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_spmm_special_cta -s 2 -c 1 -o gpurun_out/special_full -f \
+  python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu5.log 2>&1
+timeout 600 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+tail -1 gpurun_out/bench_reference.json | cut -c1-300
