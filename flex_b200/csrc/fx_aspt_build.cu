@@ -559,7 +559,10 @@ int aspt_build(fx_tiles* t, cudaStream_t s) {
   FX_LAUNCH_CHECK();
   // Heaviest entries first only when the grid is a few waves long (a.G = 2 CTAs per SM, the row kernel runs 3): there the
   // tail is what counts (flickr-shape, 698 panels: 0.087 -> 0.073 ms); on long grids the panel order is worth more, because
-  // neighbouring panels share B rows in L2 (yelp-shape 0.576 -> 0.593 ms, Amazon-shape 6.55 -> 7.34 ms; Reddit-shape equal)
+  // neighbouring panels share B rows in L2 (yelp-shape 0.576 -> 0.593 ms, Amazon-shape 6.55 -> 7.34 ms; Reddit-shape equal).
+  // (tried on long grids: cutting the panels of the last wave in four and of the wave before in two, to shorten the tail
+  // (12 % of the row kernel's SM time on Reddit-shape) -- each part repeats the panel prologue and it only costs:
+  // Reddit-shape 0.536 -> 0.577 ms, yelp-shape 0.577 -> 0.614, Amazon-shape 6.58 -> 6.76)
   static const int wl_env = getenv("FLEX_WL_CLASSES") ? std::max(1, std::min(4, atoi(getenv("FLEX_WL_CLASSES")))) : 0;
   const int wl_classes = wl_env ? wl_env : (a.npanel <= 3 * heavy_ctas(1 << 30) ? 4 : 1);
   k_worklist<<<1, 1024, 0, s>>>(nullptr, 0, a.csr_v, a.spec_off, a.nr, a.npanel, a.wl_all, a.wl_cap, a.stats, a.stats + 8, wl_classes);
