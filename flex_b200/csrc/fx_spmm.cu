@@ -349,7 +349,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
     if (TILES && (o & 0x80000000u)) return S4[o & 0x7fffffffu];
     return ldg4_keep_at(B4, o, pol.keep);
   };
-  uint32_t* sb0 = sbuf + (size_t)w * 4 * LPR;  // [2 buffers][offsets LPR | values LPR]
+  // A worker stages CH = 32 nz per chunk whatever its width: at k = 32 (8 lanes per row) a lane brings in four nz, so the
+  // chunk's fixed cost (metadata request, staging, the tile barrier) is paid per 32 nz and not per 8
+  constexpr int CH = 32, EPL = CH / LPR;
+  uint32_t* sb0 = sbuf + (size_t)w * 4 * CH;  // [2 buffers][offsets CH | values CH]
   int buf = 0;
   // one group: M*4 B rows requested back to back, then their FMAs in nz order
   auto group = [&](auto mtag, const uint32_t* so, float4& acc) {
@@ -362,14 +365,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
     }
 #pragma unroll
     for (int q = 0; q < M; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(so + LPR + 4 * q);
+      const float4 v = *reinterpret_cast<const float4*>(so + CH + 4 * q);
       fma4(acc, v.x, b[4 * q]); fma4(acc, v.y, b[4 * q + 1]); fma4(acc, v.z, b[4 * q + 2]); fma4(acc, v.w, b[4 * q + 3]);
     }
   };
   // two passes over the panel's rows, each through its own counter: the long rows first, so that no
   // worker starts one when the others are about to run out of rows
   constexpr int LONG_ROW = 96;
-  constexpr int GM = (G < LPR ? G : LPR) / 4;  // quads per full group
+  constexpr int GM = (G < CH ? G : CH) / 4;  // quads per full group
   int pass = 0;
   auto grab = [&](int& Lr) -> int {  // next row of this pass (its handled length in Lr), -1 when the panel is done
     for (;;) {
@@ -385,15 +388,35 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
       if ((Lr >= LONG_ROW) == (pass == 0)) return r;
     }
   };
-  // (column, value) of this lane's nz in the row's chunk at i; lanes past the end repeat the chunk's last nz (masked to
-  // value 0 when staged): every staged entry is a valid B row and the tail group is padded without branches
-  auto meta = [&](int rr, int LL, int i, int& cc, float& vv) {
-    const int e = RS[rr] + i + min(sl, min(LPR, LL - i) - 1);
-    cc = ldg_stream(a.csr_e + e, pol.stream);
-    vv = ldg_stream(a.csr_ev + e, pol.stream);
+  // stage the chunk of row rr that starts at nz i: lane sl brings in nz sl, sl + LPR, ... ; entries past the end repeat the
+  // chunk's last nz with value 0, so every staged entry is a valid B row and the tail group is padded without branches
+  auto stage = [&](int rr, int i, int cnt, uint32_t* sb) {
+    int cc[EPL];
+    float vv[EPL];
+    const int e0 = RS[rr] + i;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      const int e = e0 + min(sl + j * LPR, cnt - 1);
+      cc[j] = ldg_stream(a.csr_e + e, pol.stream);
+      vv[j] = ldg_stream(a.csr_ev + e, pol.stream);
+    }
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      unsigned off = (unsigned)cc[j] * k4;
+      if (TILES && ntres > 0) {
+        const int e = e0 + min(sl + j * LPR, cnt - 1);
+        const int base = cnt0 * BH + rr * delta;
+        if (e < a.mcsr_e[base + ntres]) {
+          int g = 0;
+          for (int b = 1; b < ntres; ++b) g += e >= a.mcsr_e[base + b];
+          off = 0x80000000u | (unsigned)((g * BW + (cc[j] & (BW - 1))) * (KC / 4));
+        }
+      }
+      sb[sl + j * LPR] = off;
+      sb[CH + sl + j * LPR] = sl + j * LPR < cnt ? __float_as_uint(vv[j]) : 0u;
+    }
   };
-  int L = 0, c = 0;
-  float v = 0.f;
+  int L = 0;
   // (tried: taking the next row and requesting its first metadata before this row's B requests go out -- 0.597 vs
   // 0.564 ms on Reddit-shape k=128 at the same 40 registers; rows of different workers already overlap)
   for (int r = grab(L); r >= 0; r = grab(L)) {
@@ -401,22 +424,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
     // latency runs under the metadata and B requests instead of ending the row)
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tslot >= 0) acc = ldg4_stream(reinterpret_cast<const float4*>(a.tc_out) + ((size_t)tslot * BH + r) * k4 + c4, pol.stream);
-    for (int i = 0; i < L; i += LPR) {
-      const int cnt = min(LPR, L - i);
-      meta(r, L, i, c, v);
-      unsigned off = (unsigned)c * k4;
-      if (TILES && ntres > 0) {
-        const int e = RS[r] + i + min(sl, cnt - 1);
-        const int base = cnt0 * BH + r * delta;
-        if (e < a.mcsr_e[base + ntres]) {
-          int g = 0;
-          for (int b = 1; b < ntres; ++b) g += e >= a.mcsr_e[base + b];
-          off = 0x80000000u | (unsigned)((g * BW + (c & (BW - 1))) * (KC / 4));
-        }
-      }
-      uint32_t* sb = sb0 + buf * 2 * LPR;
-      sb[sl] = off;
-      sb[LPR + sl] = sl < cnt ? __float_as_uint(v) : 0u;
+    for (int i = 0; i < L; i += CH) {
+      const int cnt = min(CH, L - i);
+      uint32_t* sb = sb0 + buf * 2 * CH;
+      stage(r, i, cnt, sb);
       tile.sync();
       int q4 = (cnt + 3) >> 2;  // quads of this chunk, the last one padded
       const uint32_t* so = sb;
@@ -542,7 +553,7 @@ template <int KC, int WARPS, int MINB, int G, bool TILES>
 static int launch_one(PanelArgs a, const int* plist, int npan, const int2* wl, int nwl, int kchunks, size_t tile_smem,
                       cudaStream_t s) {
   constexpr int NW = WARPS * (32 / (KC / 4));
-  const size_t smem = tile_smem + (size_t)NW * 4 * (KC / 4) * sizeof(uint32_t);  // + per-worker offset / value staging
+  const size_t smem = tile_smem + (size_t)NW * 4 * 32 * sizeof(uint32_t);  // + per-worker offset / value staging (2 x 32 nz)
   static const bool no_wl = getenv("FLEX_NO_WORKLIST") != nullptr;
   // a uniform split (few panels, or FLEX_SPLIT) keeps the blockIdx mapping; otherwise the build's work list
   a.wl = (a.split == 1 && wl && nwl > 0 && !no_wl) ? wl : nullptr;
