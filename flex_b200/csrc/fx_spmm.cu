@@ -168,6 +168,7 @@ struct PanelArgs {
   const float* tc_out;  // [ntc][128][k]
   const int* tc_slot;   // [npanel] position in tc_out or -1; nullptr = no windows
   int hints;            // L2 eviction priorities (make_policies)
+  int team_row;         // rows of at least this many handled nz go to a team of four warps; 0 = by width (k_spmm_rows)
 };
 
 // ---- long-row chunks: partial[i,:] = sum over the i-th 512-nz chunk --------------------------
@@ -256,12 +257,17 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special_cta(PanelArgs
 template <int KC, int WARPS, bool TILES, int MINB, int G>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, const int* __restrict__ plist) {
   constexpr int LPR = KC / 4, RPW = 32 / LPR;  // NW = WARPS * RPW workers per CTA
+  // rows of >= TEAM_ROW nz are shared by a team of four warps, rows of >= LONG_ROW are taken before the short ones
+  constexpr int LONG_ROW = 96;
+  const int TEAM_ROW = a.team_row > 0 ? a.team_row : ((1024 / (4 * RPW)) > LONG_ROW ? 1024 / (4 * RPW) : LONG_ROW);
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // dynamic shared memory: [TILES: TS*BW*KC floats] [sbuf: NW * 2 buffers * (LPR offsets + LPR values)]
+  // dynamic shared memory: [TILES: TS*BW*KC floats] [sbuf: NW * 2 buffers * (32 offsets + 32 values)] [team_acc: NW * KC floats]
   float* stile = reinterpret_cast<float*>(smem_raw);  // [TS][BW][KC]
   uint32_t* sbuf = reinterpret_cast<uint32_t*>(reinterpret_cast<float*>(smem_raw) + (TILES ? (size_t)a.TS * a.BW * KC : 0));
   __shared__ int P[BH + 1], RS[BH];
-  __shared__ int next_row, next_row2;
+  __shared__ int next_row, next_row2, next_team;
+  __shared__ int long_list[BH], n_long;  // rows of this CTA with >= TEAM_ROW handled nz (any order)
+  __shared__ int team_row[WARPS / 4];
   __shared__ uint64_t bar;
   auto tile = cg::tiled_partition<LPR>(cg::this_thread_block());
   const int sl = tile.thread_rank();
@@ -339,7 +345,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid] < thi) lo = mid + 1; else hi = mid; }
     rhi = part_q == split - 1 ? BH : lo;
   }
-  if (threadIdx.x == 0) { next_row = rlo; next_row2 = rlo; }
+  if (threadIdx.x == 0) { next_team = 0; next_row = rlo; next_row2 = rlo; n_long = 0; }
+  __syncthreads();
+  for (int r = rlo + threadIdx.x; r < rhi; r += blockDim.x)
+    if ((split > 1 ? P[r + 1] - P[r] : P[r + 1]) >= TEAM_ROW) long_list[atomicAdd(&n_long, 1)] = r;
   __syncthreads();
   if (TILES && ntres > 0) mbar_wait(&bar, 0);
 
@@ -369,10 +378,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
       fma4(acc, v.x, b[4 * q]); fma4(acc, v.y, b[4 * q + 1]); fma4(acc, v.z, b[4 * q + 2]); fma4(acc, v.w, b[4 * q + 3]);
     }
   };
-  // two passes over the panel's rows, each through its own counter: the long rows first, so that no
-  // worker starts one when the others are about to run out of rows
-  constexpr int LONG_ROW = 96;
+  // Three passes over the panel's rows.  The longest rows (>= TEAM_ROW nz: 256 at k = 128, 96 at k = 32) first, each by a
+  // TEAM of four warps (U = 4 * RPW workers): worker u takes the row's chunks u, u + U, ..., the partial sums meet in shared
+  // memory and worker 0 adds them in worker order and stores the row.  One worker alone streams a 500-nz row as 16 chunks of
+  // dependent memory round trips (~90 us, longer than the rest of its panel takes), which made those rows the critical path
+  // of their CTAs (yelp-shape k=32: 0.44 -> 0.28 ms).  Then single workers take whole rows from shared counters, rows of
+  // >= LONG_ROW nz before the short ones so that none starts when the others run out of rows.
   constexpr int GM = (G < CH ? G : CH) / 4;  // quads per full group
+  constexpr int TW = 4, U = TW * RPW;
+  static_assert(WARPS % TW == 0, "teams of four warps");
   int pass = 0;
   auto grab = [&](int& Lr) -> int {  // next row of this pass (its handled length in Lr), -1 when the panel is done
     for (;;) {
@@ -385,7 +399,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
         continue;
       }
       Lr = split > 1 ? P[r + 1] - P[r] : P[r + 1];
-      if ((Lr >= LONG_ROW) == (pass == 0)) return r;
+      if (Lr < TEAM_ROW && (Lr >= LONG_ROW) == (pass == 0)) return r;
     }
   };
   // stage the chunk of row rr that starts at nz i: lane sl brings in nz sl, sl + LPR, ... ; entries past the end repeat the
@@ -416,15 +430,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
       sb[CH + sl + j * LPR] = sl + j * LPR < cnt ? __float_as_uint(vv[j]) : 0u;
     }
   };
-  int L = 0;
-  // (tried: taking the next row and requesting its first metadata before this row's B requests go out -- 0.597 vs
-  // 0.564 ms on Reddit-shape k=128 at the same 40 registers; rows of different workers already overlap)
-  for (int r = grab(L); r >= 0; r = grab(L)) {
-    // the accumulator starts from the row's tensor-window product (requested here, needed by the first FMA: its
-    // latency runs under the metadata and B requests instead of ending the row)
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tslot >= 0) acc = ldg4_stream(reinterpret_cast<const float4*>(a.tc_out) + ((size_t)tslot * BH + r) * k4 + c4, pol.stream);
-    for (int i = 0; i < L; i += CH) {
+  // acc += chunks first, first + stride, ... of row r (handled length L)
+  auto run_chunks = [&](int r, int L, int first, int stride, float4& acc) {
+    for (int i = first * CH; i < L; i += stride * CH) {
       const int cnt = min(CH, L - i);
       uint32_t* sb = sb0 + buf * 2 * CH;
       stage(r, i, cnt, sb);
@@ -439,7 +447,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
       }
       buf ^= 1;
     }
-    // add the row's 512-chunk partials (chunk order), store once
+  };
+  // acc (+ the row's 512-chunk partials, in chunk order) -> C, every element written once
+  auto finish_row = [&](int r, float4 acc) {
     const int row = p * BH + r;
     if (a.spec_off) {
       const int so = a.spec_off[row], nch = a.spec_off[row + 1] - so;
@@ -450,6 +460,48 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
       }
     }
     if (col_ok && row < a.nloc) stg4_stream(C4 + (size_t)row * k4, acc, pol.stream);
+  };
+  // the accumulator starts from the row's tensor-window product (requested first, needed by the first FMA: its latency
+  // runs under the metadata and B requests instead of ending the row)
+  auto start_acc = [&](int r) -> float4 {
+    if (tslot >= 0) return ldg4_stream(reinterpret_cast<const float4*>(a.tc_out) + ((size_t)tslot * BH + r) * k4 + c4, pol.stream);
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+
+  if (n_long > 0) {  // uniform over the CTA
+    const int team = warp / TW, u = (warp % TW) * RPW + sub;
+    float4* tacc = reinterpret_cast<float4*>(sbuf + (size_t)WARPS * RPW * 4 * CH) + (size_t)team * U * LPR;  // [U][LPR]
+    const int nl = n_long;
+    for (;;) {
+      if (warp % TW == 0 && lane == 0) team_row[team] = atomicAdd(&next_team, 1);
+      __syncwarp();  // the team barrier is taken by whole warps
+      asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TW * 32) : "memory");
+      const int li = team_row[team];
+      if (li >= nl) break;
+      const int r = long_list[li];
+      const int L = split > 1 ? P[r + 1] - P[r] : P[r + 1];
+      float4 acc = u == 0 ? start_acc(r) : make_float4(0.f, 0.f, 0.f, 0.f);
+      run_chunks(r, L, u, U, acc);
+      if (u != 0) tacc[u * LPR + sl] = acc;
+      __syncwarp();  // the team barrier is taken by whole warps
+      asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TW * 32) : "memory");
+      if (u == 0) {
+        for (int q = 1; q < U; ++q) {
+          const float4 x = tacc[q * LPR + sl];
+          acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+        }
+        finish_row(r, acc);
+      }
+      // tacc and team_row are rewritten only after the next bar.sync pair, which worker 0 joins after its reads
+    }
+  }
+  // (tried: taking the next row and requesting its first metadata before this row's B requests go out -- 0.597 vs
+  // 0.564 ms on Reddit-shape k=128 at the same 40 registers; rows of different workers already overlap)
+  int L = 0;
+  for (int r = grab(L); r >= 0; r = grab(L)) {
+    float4 acc = start_acc(r);
+    run_chunks(r, L, 0, 1, acc);
+    finish_row(r, acc);
   }
 }
 
@@ -553,7 +605,8 @@ template <int KC, int WARPS, int MINB, int G, bool TILES>
 static int launch_one(PanelArgs a, const int* plist, int npan, const int2* wl, int nwl, int kchunks, size_t tile_smem,
                       cudaStream_t s) {
   constexpr int NW = WARPS * (32 / (KC / 4));
-  const size_t smem = tile_smem + (size_t)NW * 4 * 32 * sizeof(uint32_t);  // + per-worker offset / value staging (2 x 32 nz)
+  // + per-worker offset / value staging (2 x 32 nz) + the teams' partial sums of long rows (one row of C per worker)
+  const size_t smem = tile_smem + (size_t)NW * 4 * 32 * sizeof(uint32_t) + (size_t)NW * KC * sizeof(float);
   static const bool no_wl = getenv("FLEX_NO_WORKLIST") != nullptr;
   // a uniform split (few panels, or FLEX_SPLIT) keeps the blockIdx mapping; otherwise the build's work list
   a.wl = (a.split == 1 && wl && nwl > 0 && !no_wl) ? wl : nullptr;
@@ -637,6 +690,8 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   a.tc_out = nullptr; a.tc_slot = nullptr; a.wl = nullptr;
   static const int hints = getenv("FLEX_HINTS") ? atoi(getenv("FLEX_HINTS")) : 1;
   a.hints = hints;
+  static const int team_row = getenv("FLEX_TEAM_ROW") ? atoi(getenv("FLEX_TEAM_ROW")) : 0;
+  a.team_row = team_row;
   if (t->format == FX_FMT_TCW && t->tcw.ntc > 0) {  // tensor windows first; the panel kernel adds them in
     const fx_tcw_dev& w = t->tcw;
     fxtc::TcArgs ta;
