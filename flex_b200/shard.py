@@ -38,3 +38,39 @@ def gather_rows(dist, local_rows, shards, k, device=None):
     outs = [torch.empty_like(pad) for _ in shards]
     dist.all_gather(outs, pad)
     return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(outs, shards)], 0)
+
+
+class ShardedHostSpmm:
+    """C = A*B from HOST buffers on G ranks without sending B over PCIe G times.
+
+    `fx_spmm_host` on every rank copies all of B to its GPU (B is replicated), so at G ranks the host
+    feeds G * n*k*4 bytes through its PCIe root per SpMM and the end-to-end time grows with G (8 GPUs,
+    Reddit-shape k=128: 5.96 ms against 3.81 ms on one).  Here rank r uploads only rows
+    [r*ceil(n/G), (r+1)*ceil(n/G)) of B, the slices are all-gathered between the GPUs (NCCL over NVLink:
+    the one real exchange step of the sharded path, SURVEY.md 8e "upload once per rank or ncclBroadcast"),
+    every rank multiplies its row-panel shard and copies its own rows of C back.
+
+    `spmm(B_full_tensor, C_local_tensor)` is the device multiply (Mat.spmm through the C ABI on the GPU;
+    the CPU tests pass the oracle).  Buffers are allocated once; `__call__` is one step."""
+
+    def __init__(self, dist, n, k, rank, world, device, spmm, n_local_rows):
+        import torch
+        self.dist, self.n, self.k, self.rank, self.world, self.spmm = dist, n, k, rank, world, spmm
+        self.rows_per = (n + world - 1) // world
+        self.lo = min(n, rank * self.rows_per)
+        self.hi = min(n, self.lo + self.rows_per)
+        self.B_full = torch.zeros((self.rows_per * world, k), dtype=torch.float32, device=device)
+        self.stage = torch.zeros((self.rows_per, k), dtype=torch.float32, device=device)
+        self.C_local = torch.empty((n_local_rows, k), dtype=torch.float32, device=device)
+
+    def h2d_bytes(self):
+        return 4 * (self.hi - self.lo) * self.k
+
+    def __call__(self, B_host_slice, C_host_out):
+        """B_host_slice: this rank's rows [lo, hi) of B (pinned host tensor); C_host_out: pinned, [n_local_rows, k]."""
+        if self.hi > self.lo:
+            self.stage[: self.hi - self.lo].copy_(B_host_slice, non_blocking=True)
+        self.dist.all_gather_into_tensor(self.B_full, self.stage)
+        self.spmm(self.B_full, self.C_local)
+        C_host_out.copy_(self.C_local, non_blocking=True)
+        return C_host_out

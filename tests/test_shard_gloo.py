@@ -39,6 +39,53 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def _worker_host(rank, world, port, ret):
+    """ShardedHostSpmm (bench.py's end-to-end path at N > 1): B arrives in row slices, one per rank."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from flex_b200.shard import ShardedHostSpmm, gather_rows, panel_shards
+    from oracle import orc
+    from util import random_csr, rand_dense
+    n, k = 1501, 8  # n not a multiple of the world size: the last slice is short
+    rp, c, v = random_csr(n, 7, 11, hubs=2)
+    B = rand_dense(n, k, 2)
+    shards = panel_shards(rp, world)
+    lo, hi = shards[rank]
+    sub = (rp[lo:hi + 1] - rp[lo]).astype(np.uint32)
+
+    def spmm(B_full, C_local):
+        Bn = np.ascontiguousarray(B_full.numpy()[:n])
+        if hi > lo:
+            C_local.copy_(torch.from_numpy(orc.spmm_ref(sub, c[rp[lo]:rp[hi]], v[rp[lo]:rp[hi]], Bn)))
+
+    run = ShardedHostSpmm(dist, n, k, rank, world, torch.device("cpu"), spmm, hi - lo)
+    Ch = torch.empty((hi - lo, k), dtype=torch.float32)
+    for _ in range(2):  # buffers are reused between steps
+        run(torch.from_numpy(B[run.lo:run.hi]), Ch)
+    full = gather_rows(dist, Ch, shards, k).numpy()
+    ok = np.array_equal(full, orc.spmm_ref(rp, c, v, B)) and np.array_equal(run.B_full.numpy()[:n], B)
+    t = torch.tensor([int(ok)])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put(int(t.item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_host_spmm_gloo(world):
+    from oracle import orc
+    orc.build()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29700 + world + (os.getpid() % 200)
+    procs = [ctx.Process(target=_worker_host, args=(r, world, port, ret)) for r in range(world)]
+    [p.start() for p in procs]
+    ok = ret.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert ok == 1
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_spmm_gloo(world):
     from oracle import orc
