@@ -222,6 +222,57 @@ def workload_config(args, k, n, nnz):
             "parallelism": f"row-panel shards x{args.gpus}, B replicated"}
 
 
+def e2e_sharded(dist, mat, Bh, Ch, n, k, lo, hi, rank, world, dev, steps, sync_all):
+    """End to end at N > 1: B is uploaded once per JOB (rank r sends rows r*ceil(n/N)... of it), all-gathered over NVLink,
+    and every rank multiplies its row-panel shard (flex_b200/shard.py:ShardedHostSpmm).  fx_spmm_host on every rank pushes
+    all of B through the host's PCIe root N times; the caller keeps that time as e2e.replicated_ms.  `Ch` holds the
+    fx_spmm_host result of this rank's shard and is the check.  Returns (ms per step as the max over ranks or None,
+    H2D bytes per rank, note)."""
+    import torch
+    cuda = dev.type == "cuda"
+    try:
+        from flex_b200.shard import ShardedHostSpmm
+        stream = torch.cuda.current_stream().cuda_stream if cuda else None
+        run = ShardedHostSpmm(dist, n, k, rank, world, dev,
+                              lambda Bf, Cl: mat.spmm(Bf.data_ptr(), Cl.data_ptr(), k, stream=stream), hi - lo)
+        Bslice = Bh[run.lo:run.hi]
+        Ch2 = torch.empty((hi - lo, k), dtype=torch.float32)
+        if cuda:
+            Ch2 = Ch2.pin_memory()
+        for _ in range(2):
+            run(Bslice, Ch2)
+            if cuda:
+                torch.cuda.synchronize()
+        # same kernels, but fx_spmm_host multiplies two 64-column halves (other worker teams, other summation order)
+        same = torch.tensor([int(torch.allclose(Ch2, Ch, rtol=1e-4, atol=1e-4))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        sync_all()
+        tot = 0.0
+        if cuda:
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(steps):
+            if cuda:
+                s0.record()
+                run(Bslice, Ch2)
+                s1.record()
+                s1.synchronize()
+                tot += s0.elapsed_time(s1)
+            else:
+                t0 = time.perf_counter()
+                run(Bslice, Ch2)
+                tot += (time.perf_counter() - t0) * 1e3
+        sh = torch.tensor([tot / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(sh, op=dist.ReduceOp.MAX)
+        if int(same.item()) != 1:
+            return None, None, "sharded-input path disagreed with fx_spmm_host: not used"
+        return sh.item(), int(run.h2d_bytes()), (
+            "B uploaded once per job: each rank copies its 1/N row slice from pinned host memory, NCCL all-gather over NVLink, "
+            "SpMM of the rank's row-panel shard, D2H of its rows of C; bytes are per rank; result checked against "
+            "fx_spmm_host on every rank (1e-4)")
+    except Exception as ex:  # keep the replicated number
+        return None, None, "sharded-input path failed: %r" % (ex,)
+
+
 def main():
     args = parse()
     k = args.k or DEFAULT_K.get(args.workload, 128)
@@ -336,42 +387,9 @@ def main():
     e2e_ms = e2e_ms.item()
     e2e_h2d, e2e_note, e2e_replicated_ms = int(4 * n * k), None, None
     if dist is not None:
-        # N > 1: B is uploaded once per JOB (rank r sends rows r*ceil(n/N)... of it), all-gathered over NVLink, and every
-        # rank multiplies its row-panel shard (flex_b200/shard.py:ShardedHostSpmm).  fx_spmm_host on every rank (above)
-        # pushes all of B through the host's PCIe root N times; its time is kept as e2e.replicated_ms.
-        try:
-            from flex_b200.shard import ShardedHostSpmm
-            cur = torch.cuda.current_stream()
-            run = ShardedHostSpmm(dist, n, k, rank, world, dev,
-                                  lambda Bf, Cl: mat.spmm(Bf.data_ptr(), Cl.data_ptr(), k, stream=cur.cuda_stream), hi - lo)
-            Bslice = Bh[run.lo:run.hi]
-            Ch2 = torch.empty((hi - lo, k), dtype=torch.float32).pin_memory()
-            for _ in range(2):
-                run(Bslice, Ch2)
-                torch.cuda.synchronize()
-            # same kernels, but fx_spmm_host multiplies two 64-column halves (other worker teams, other summation order)
-            same = torch.tensor([int(torch.allclose(Ch2, Ch, rtol=1e-4, atol=1e-4))], device=dev)
-            dist.all_reduce(same, op=dist.ReduceOp.MIN)
-            sync_all()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            tot = 0.0
-            for _ in range(e2e_steps):
-                s0.record()
-                run(Bslice, Ch2)
-                s1.record()
-                s1.synchronize()
-                tot += s0.elapsed_time(s1)
-            sh = torch.tensor([tot / e2e_steps], dtype=torch.float64, device=dev)
-            dist.all_reduce(sh, op=dist.ReduceOp.MAX)
-            if int(same.item()) == 1:
-                e2e_replicated_ms, e2e_ms, e2e_h2d = e2e_ms, sh.item(), int(run.h2d_bytes())
-                e2e_note = ("B uploaded once per job: each rank copies its 1/N row slice from pinned host memory, NCCL all-gather "
-                            "over NVLink, SpMM of the rank's row-panel shard, D2H of its rows of C; bytes are per rank; "
-                            "result checked against fx_spmm_host on every rank (1e-4)")
-            else:
-                e2e_note = "sharded-input path disagreed with fx_spmm_host: not used"
-        except Exception as ex:  # keep the replicated number
-            e2e_note = "sharded-input path failed: %r" % (ex,)
+        sh_ms, sh_h2d, e2e_note = e2e_sharded(dist, mat, Bh, Ch, n, k, lo, hi, rank, world, dev, e2e_steps, sync_all)
+        if sh_ms is not None:
+            e2e_replicated_ms, e2e_ms, e2e_h2d = e2e_ms, sh_ms, sh_h2d
 
     ag_ms = None
     if args.allgather and dist is not None:

@@ -72,6 +72,60 @@ def _worker_host(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+class _CpuMat:
+    """Stand-in for flex_b200.Mat on the CPU ranks: spmm(B_ptr, C_ptr, k) over raw pointers, through the oracle."""
+
+    def __init__(self, sub, c, v, n, rows):
+        self.sub, self.c, self.v, self.n, self.rows = sub, c, v, n, rows
+
+    def spmm(self, B_ptr, C_ptr, k, stream=None):
+        import ctypes
+        from oracle import orc
+        Bf = np.ctypeslib.as_array(ctypes.cast(B_ptr, ctypes.POINTER(ctypes.c_float)), shape=(self.n, k))
+        if self.rows:
+            Cl = np.ctypeslib.as_array(ctypes.cast(C_ptr, ctypes.POINTER(ctypes.c_float)), shape=(self.rows, k))
+            Cl[:] = orc.spmm_ref(self.sub, self.c, self.v, np.ascontiguousarray(Bf))
+
+
+def _worker_bench(rank, world, port, ret):
+    """bench.py's e2e leg at N > 1 (bench.e2e_sharded) end to end on gloo: names, shapes, the check and the reduction."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    from flex_b200.shard import panel_shards
+    from oracle import orc
+    from util import random_csr, rand_dense
+    n, k = 1333, 8
+    rp, c, v = random_csr(n, 6, 13, hubs=2)
+    B = rand_dense(n, k, 3)
+    lo, hi = panel_shards(rp, world)[rank]
+    sub = (rp[lo:hi + 1] - rp[lo]).astype(np.uint32)
+    cs, vs = c[rp[lo]:rp[hi]], v[rp[lo]:rp[hi]]
+    mat = _CpuMat(sub, cs, vs, n, hi - lo)
+    Ch = torch.from_numpy(orc.spmm_ref(sub, cs, vs, B) if hi > lo else np.zeros((0, k), np.float32))
+    ms, h2d, note = bench.e2e_sharded(dist, mat, torch.from_numpy(B), Ch, n, k, lo, hi, rank, world, torch.device("cpu"), 2,
+                                      dist.barrier)
+    if rank == 0:
+        ret.put((ms, h2d, note))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bench_e2e_sharded_gloo():
+    from oracle import orc
+    orc.build()
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29900 + (os.getpid() % 200)
+    procs = [ctx.Process(target=_worker_bench, args=(r, world, port, ret)) for r in range(world)]
+    [p.start() for p in procs]
+    ms, h2d, note = ret.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert ms is not None and ms > 0, note
+    assert h2d == 4 * 667 * 8 and "once per job" in note
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_host_spmm_gloo(world):
     from oracle import orc
