@@ -430,11 +430,21 @@ __global__ void k_fill_special(const int* __restrict__ spec_cnt, const int* __re
 
 namespace fx {
 
-static int heavy_ctas(int npanel) {
+static int sm_count() {
   int dev = 0, sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+  return sm;
+}
+
+static int heavy_ctas(int npanel) {
+  const int sm = sm_count();
   int g = 2 * sm;  // 3 per SM measured no better (tPre 3.89 vs 4.07 ms TCW, 1.83 vs 1.73 ms ASpT on Reddit-shape)
+  // FLEX_BUILD_CTAS: persistent CTAs of the counting kernels.  Every CTA owns one counter per column (4 B x ncols), so the
+  // default is 276 MB of counters on Reddit-shape -- more than L2; fewer CTAs trade parallelism for L2-resident counters
+  // (unmeasured: added after the round's GPU budget was spent)
+  static const int g_env = getenv("FLEX_BUILD_CTAS") ? atoi(getenv("FLEX_BUILD_CTAS")) : 0;
+  if (g_env > 0) g = g_env;
   return npanel < g ? (npanel > 0 ? npanel : 1) : g;
 }
 
@@ -557,14 +567,14 @@ int aspt_build(fx_tiles* t, cudaStream_t s) {
   FX_LAUNCH_CHECK();
   k_fill_special<<<ceil_div(a.nr, 256), 256, 0, s>>>(a.spec_cnt, a.spec_off, a.nr, a.special, a.special2);
   FX_LAUNCH_CHECK();
-  // Heaviest entries first only when the grid is a few waves long (a.G = 2 CTAs per SM, the row kernel runs 3): there the
+  // Heaviest entries first only when the grid is a few waves long (at most 6 panels per SM; the row kernel runs 3 CTAs per SM): there the
   // tail is what counts (flickr-shape, 698 panels: 0.087 -> 0.073 ms); on long grids the panel order is worth more, because
   // neighbouring panels share B rows in L2 (yelp-shape 0.576 -> 0.593 ms, Amazon-shape 6.55 -> 7.34 ms; Reddit-shape equal).
   // (tried on long grids: cutting the panels of the last wave in four and of the wave before in two, to shorten the tail
   // (12 % of the row kernel's SM time on Reddit-shape) -- each part repeats the panel prologue and it only costs:
   // Reddit-shape 0.536 -> 0.577 ms, yelp-shape 0.577 -> 0.614, Amazon-shape 6.58 -> 6.76)
   static const int wl_env = getenv("FLEX_WL_CLASSES") ? std::max(1, std::min(4, atoi(getenv("FLEX_WL_CLASSES")))) : 0;
-  const int wl_classes = wl_env ? wl_env : (a.npanel <= 3 * heavy_ctas(1 << 30) ? 4 : 1);
+  const int wl_classes = wl_env ? wl_env : (a.npanel <= 6 * sm_count() ? 4 : 1);
   k_worklist<<<1, 1024, 0, s>>>(nullptr, 0, a.csr_v, a.spec_off, a.nr, a.npanel, a.wl_all, a.wl_cap, a.stats, a.stats + 8, wl_classes);
   FX_LAUNCH_CHECK();
   if (a.any_flag) {  // the tiled launch and the plain launch walk their own panel lists (counts are on the device)
