@@ -4,7 +4,9 @@
 // B loads and fp32 atomics into a pre-zeroed C -- aspt/sspmm_128.cu:321-427,703-827):
 //   * a row of C is owned by LPR = KC/4 lanes; each lane keeps one float4 of the row in registers,
 //     so a B row is fetched with one 128-bit load per lane (512 B per warp instruction at k=128);
-//   * (col,val) pairs are read coalesced, LPR at a time, and broadcast with warp shuffles;
+//   * (col,val) pairs are read coalesced, 32 nz at a time, staged per worker in shared memory as (B-row offset, value)
+//     and read back four at a time with broadcast LDS.128 (the 512-chunk kernel broadcasts with warp shuffles);
+//   * B rows carry an evict_last L2 policy, the streams read or written once bypass L1 and carry evict_first;
 //   * a panel's dense tiles are staged in shared memory once per CTA by the TMA unit
 //     (cp.async.bulk global->shared, completion on an mbarrier), one 16-byte-aligned row of B per
 //     bulk copy, and read back with 128-bit shared loads;
@@ -239,11 +241,12 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special_cta(PanelArgs
 // The panel's handled nz are every row's [dense groups | sparse tail], i.e. everything except the
 // 512-chunks k_spmm_special takes from the END of long sparse groups.  A worker (LPR lanes = one row of
 // C, each lane a float4 of features) owns whole rows: it grabs the next row of the panel from a
-// shared-memory counter (long rows in a first pass, so none starts when the others run out), streams
-// the row's nz in chunks of LPR -- metadata staged as (offset,value) pairs in a per-worker shared
-// buffer and read back two nz per broadcast LDS.128, B rows fetched with 128-bit loads, FFMA2 -- adds
-// the row's 512-chunk partials and its tensor-window product and stores the row once: every C element
-// is written exactly once, in a fixed summation order, without atomics.
+// shared-memory counter (long rows in a first pass, so none starts when the others run out; the longest
+// rows are shared by teams of four warps, see the three passes below), streams the row's nz in chunks of
+// 32 -- metadata staged as offsets and values in a per-worker shared buffer and read back four nz per
+// broadcast LDS.128, B rows fetched with 128-bit loads, FFMA2 -- starting from the row's tensor-window
+// product, adds the row's 512-chunk partials and stores the row once: every C element is written exactly
+// once, in a fixed summation order, without atomics.
 // (Round-1 history: an nz-balanced variant -- workers take equal slices of the panel's nz stream, rows
 // looked up per nz through a prefix table, shared rows reduced through shared memory -- needed ~3x the
 // instructions per nz on short rows: 0.729 ms vs 0.634 ms on Reddit-shape)
