@@ -431,6 +431,20 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
+        try:
+            # second view of the same step: the bytes the SMs must pull through the L2->SM crossbar (the path that binds,
+            # DESIGN.md section 5) -- one B row per gathered nz, one per listed window column, tc_out out and back, A, C --
+            # against the rate the 512-chunk kernel sustains on this access pattern (18.3 TB/s, ncu:
+            # profiles/r1_ncu_tcw_reddit_k128.md); hits in L1 make the real transfer smaller, so this is an upper estimate
+            g_nz = tcw["rest_nnz"] if (tcw and tcw.get("ntc")) else loc_nnz
+            g_cols = tcw["listed_columns"] if (tcw and tcw.get("ntc")) else 0
+            g_tc = 2 * tcw["ntc"] * 128 * k * 4 if (tcw and tcw.get("ntc")) else 0
+            g_bytes = 4 * k * (g_nz + g_cols) + g_tc + 8 * loc_nnz + 4 * (hi - lo) * k
+            line["roofline"]["gather_path"] = {"bytes": int(g_bytes), "achieved": g_bytes / (ms_per_step * 1e-3) / 1e12,
+                                               "ceiling": 18.3, "unit": "TB/s",
+                                               "frac": g_bytes / (ms_per_step * 1e-3) / 1e12 / 18.3}
+        except Exception:
+            pass
         if e2e_note is not None:
             line["e2e"]["path"] = e2e_note
         if e2e_replicated_ms is not None:
