@@ -171,6 +171,7 @@ struct PanelArgs {
   const int* tc_slot;   // [npanel] position in tc_out or -1; nullptr = no windows
   int hints;            // L2 eviction priorities (make_policies)
   int team_row;         // rows of at least this many handled nz go to a team of four warps; 0 = by width (k_spmm_rows)
+  int tiles_ok;         // bit 31 of a staged offset is free to flag "this B row is in the shared-memory tiles"
 };
 
 // ---- long-row chunks: partial[i,:] = sum over the i-th 512-nz chunk --------------------------
@@ -631,7 +632,7 @@ static int launch_panels(const fx_aspt_dev& d, const PanelArgs& a, int kchunks, 
   // Measured on Reddit-shape (6 % of nz in tiles): 0.855 ms with the tiled CTAs, 0.759 ms without.
   const char* tiles_env = getenv("FLEX_TILES");  // "0" never, "1" always, unset = by density
   const double dense_frac = d.ne > 0 ? (double)(d.ne - d.S1) / d.ne : 0.0;
-  const bool use_tiles = tiles_env ? atoi(tiles_env) != 0 : dense_frac >= 0.25;
+  const bool use_tiles = (tiles_env ? atoi(tiles_env) != 0 : dense_frac >= 0.25) && a.tiles_ok;
   if (!use_tiles || d.n_tiled == 0)  // every panel through the L1 path (dense groups are ordinary nz there)
     return launch_one<KC, WARPS, MINB, G, false>(a, nullptr, d.npanel, d.wl_all, d.n_wl_all, kchunks, 0, s);
   if (d.n_plain > 0) {
@@ -695,6 +696,7 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   a.hints = hints;
   static const int team_row = getenv("FLEX_TEAM_ROW") ? atoi(getenv("FLEX_TEAM_ROW")) : 0;
   a.team_row = team_row;
+  a.tiles_ok = (int64_t)t->mat->n * k / 4 < (1ll << 31);
   if (t->format == FX_FMT_TCW && t->tcw.ntc > 0) {  // tensor windows first; the panel kernel adds them in
     const fx_tcw_dev& w = t->tcw;
     fxtc::TcArgs ta;
