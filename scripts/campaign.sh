@@ -26,10 +26,5 @@ b yelp_k128 --workload yelp --k 128 --steps 100 --no-cpu-baseline --cusparse
 b yelp_k128_deg --workload yelp --k 128 --steps 100 --order deg --no-cpu-baseline
 b yelp_k128_gor --workload yelp --k 128 --steps 100 --order gor --no-cpu-baseline
 b amazon_k128 --workload amazon --k 128 --steps 20 --no-cpu-baseline
-# the reference's own ASpT binary (unmodified, built for sm_100) on the headline workload
-python - <<'PY'
-import sys, time; sys.path.insert(0, ".")
-from flex_b200 import synth
-t=time.time(); rp,c,v=synth.generate("reddit", device="cuda"); synth.write_csv("/tmp/reddit_shape.csv", rp.cpu(), c.cpu(), v.cpu()); print("csv written", time.time()-t)
-PY
-for bin in sspmm_128:128 sspmm_32:32; do exe=${bin%%:*}; k=${bin##*:}; echo "== $exe reddit-shape k=$k"; timeout 600 oracle/_ref/$exe /tmp/reddit_shape.csv $k 2>&1 | grep -E "GFLOPS|t_pre|errs|vari"; done | tee $O/ref_aspt_reddit.log
+# the reference's own ASpT binary on the headline workload (context number): tests/tools/ref_aspt_context.sh
+O=$O bash tests/tools/ref_aspt_context.sh
