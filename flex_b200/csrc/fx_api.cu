@@ -175,7 +175,9 @@ extern "C" int fx_tiles_export_aspt(fx_tiles* t, fx_aspt_arrays* o) {
 static int spmm_dispatch(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s) {
   const fx_matrix* m = t->mat;
   const bool tcw = t->format == FX_FMT_TCW;
-  if (t->format == FX_FMT_CSR || (k % 4 != 0 && (t->format == FX_FMT_ASPT || tcw)) || (tcw && k > t->k)) {
+  const bool aspt_like = t->format == FX_FMT_ASPT || tcw;
+  // wider than the build's k: the per-handle scratch (512-chunk partial sums, window products) is sized for t->k
+  if (t->format == FX_FMT_CSR || (aspt_like && (k % 4 != 0 || k > t->k))) {
     // raw CSR over the shard's rows (run_ge_spmm path flex.cu:4285; "ssparse" regime :629)
     return fx::spmm_csr(m->rowptr_dev + t->row_begin, m->col_dev, m->val_dev, t->row_end - t->row_begin, B, C, k, s);
   }
@@ -220,7 +222,7 @@ extern "C" int fx_spmm_host(const fx_tiles* tc, const float* B_host, float* C_ho
   static const int want_chunks = getenv("FLEX_HOST_CHUNKS") ? atoi(getenv("FLEX_HOST_CHUNKS")) : 2;  // measured: 4.87 ms (1), 3.92 (2), 4.53 (4) on Reddit-shape k=128
   int nchunk = 1;
   if ((t->format == FX_FMT_ASPT || t->format == FX_FMT_TCW) && k % 32 == 0 && k >= 64 && want_chunks > 1 &&
-      !(t->format == FX_FMT_TCW && k > t->k)) {
+      k <= t->k) {
     nchunk = std::min(std::min(want_chunks, k / 32), 8);
     while ((k / 32) % nchunk) --nchunk;  // equal chunks, each a multiple of 32 features
   }

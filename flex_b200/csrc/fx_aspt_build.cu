@@ -544,12 +544,8 @@ int aspt_build(fx_tiles* t, cudaStream_t s) {
     a.csr_e_use = a.csr_e;
     a.csr_ev_use = a.csr_ev;
     FX_CUDA(cudaMemsetAsync(a.tcount, 0, sizeof(int) * (a.npanel + 1), s));
-    static bool attr_set = false;
-    if (!attr_set) {
-      FX_CUDA(cudaFuncSetAttribute(k_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(SORT_SMEM_CAP * sizeof(unsigned long long))));
-      attr_set = true;
-    }
+    static SmemAttr heavy_attr;
+    if (int rc = heavy_attr.ensure(k_heavy, SORT_SMEM_CAP * sizeof(unsigned long long))) return rc;
     k_heavy<<<a.G, 512, SORT_SMEM_CAP * sizeof(unsigned long long), s>>>(
         a.csr_v, col, a.mcsr_chk, a.npanel, BW, min_occ, (int)m->n, a.cnt_scratch,
         reinterpret_cast<unsigned long long*>(a.heavy), a.nheavy, a.tcount, a.key2);

@@ -77,6 +77,35 @@ struct Arena {
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev < 0 || dev >= 64) ? 0 : dev;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: the "already raised" cache is kept per device
+// ordinal (a process-wide flag made the first launch on a second GPU of the same process fail with "invalid argument").
+struct SmemAttr {
+  size_t set[64] = {};
+  template <class K>
+  int ensure(K kernel, size_t smem) {
+    if (smem <= 48 * 1024) return FX_OK;
+    const int dev = current_device();
+    if (smem > set[dev]) {
+      FX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      set[dev] = smem;
+    }
+    return FX_OK;
+  }
+};
+
+inline int sm_count_of_current_device() {
+  static int sm[64] = {};
+  const int dev = current_device();
+  if (!sm[dev]) cudaDeviceGetAttribute(&sm[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sm[dev] > 0 ? sm[dev] : 148;
+}
+
 }  // namespace fx
 
 // ---------------------------------------------------------------------------------------

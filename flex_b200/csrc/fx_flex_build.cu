@@ -337,10 +337,14 @@ __global__ void __launch_bounds__(256) k_spmm_alpha(AlphaArgs a) {
   unsigned smid;
   asm("mov.u32 %0, %%smid;" : "=r"(smid));
   const int q_own = (int)(smid % (unsigned)a.n_sm);
-  // a warp pops one pillar at a time: first from its SM's own queue, then from the shared balance queue
-  for (int phase = 0; phase < 2; ++phase) {
-    const int q = phase == 0 ? q_own : a.n_sm;
+  // A warp pops one pillar at a time: first from its SM's own queue, then from the shared balance queue (v36's order,
+  // flex.cu:4010), then it sweeps every other SM's queue.  The sweep is what makes the result independent of CTA
+  // placement: the reference relies on a CTA landing on every SM, which CUDA does not promise (a second feature chunk,
+  // opts.n_sm above the SM count, or another kernel on the GPU left queues undrained and rows of C silently zero).
+  for (int phase = 0; phase < 2 + a.n_sm; ++phase) {
+    const int q = phase == 0 ? q_own : (phase == 1 ? a.n_sm : (q_own + phase - 1) % a.n_sm);
     const unsigned qbeg = a.pillarIdx[q], qend = a.pillarIdx[q + 1];
+    if (qbeg == qend) continue;
     while (true) {
       unsigned pil = 0;
       if (lane == 0) pil = qbeg + atomicAdd(&a.counter[q * gridDim.y + blockIdx.y], 1u);
@@ -395,11 +399,7 @@ namespace fx {
 int diag_tiling_host(const fx_matrix* m, int tm, int n_sm, fx_flex_dev::PillarHost& out);
 
 static int n_sm_of(const fx_tiles* t) {
-  if (t->opts.n_sm > 0) return t->opts.n_sm;
-  int dev = 0, sm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
-  return sm;
+  return t->opts.n_sm > 0 ? t->opts.n_sm : sm_count_of_current_device();
 }
 
 int flex_carve(fx_tiles* t) {

@@ -66,6 +66,29 @@ bool parse_line(const char*& p, const char* end, std::vector<T>& out) {
   return true;
 }
 
+// fx_csr_from_device: the same column checks as validate_csr, on the device (one warp per row).  flag bit 0: a column
+// >= n; bit 1: columns of a row not strictly ascending (the GPU builders count with col[e] as an index and assume
+// ascending columns: fx_aspt_build.cu k_heavy, fx_tcw_build.cu k_tcw_select / k_tcw_split).
+__global__ void k_validate_cols(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, long long n,
+                                unsigned* __restrict__ flag) {
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const uint32_t lo = rowptr[r], hi = rowptr[r + 1];
+  unsigned bad = 0;
+  for (uint32_t e = lo + lane; e < hi; e += 32) {
+    const uint32_t c = col[e];
+    if (c >= (uint32_t)n) bad |= 1u;
+    if (e > lo && col[e - 1] >= c) bad |= 2u;
+  }
+  if (bad) atomicOr(flag, bad);
+}
+
+__global__ void k_iota(int32_t* __restrict__ p, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int32_t)i;
+}
+
 void census(fx_matrix* m) {  // DataLoader.cu:86-115
   const int64_t n = m->n, nnz = m->nnz;
   std::vector<uint32_t> tp(n + 2, 0);
@@ -235,17 +258,40 @@ extern "C" int fx_csr_from_device(int64_t n, int64_t nnz, const uint32_t* rowptr
   cudaError_t e = cudaMemcpy(m->rowptr.data(), rowptr_dev, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) { delete m; fx::set_error("rowptr D2H -> %s", cudaGetErrorString(e)); return FX_ERR_CUDA; }
   if (m->rowptr[0] != 0 || m->rowptr[n] != (uint32_t)nnz) { delete m; fx::set_error("rowPtr does not span [0,nnz]"); return FX_ERR_FORMAT; }
-  fill_info(m, name ? name : "device.csv", FX_ORDER_OVO);  // column checks need a host copy: skipped
+  for (int64_t r = 0; r < n; ++r)
+    if (m->rowptr[r] > m->rowptr[r + 1]) { delete m; fx::set_error("rowPtr not monotone at row %lld", (long long)r); return FX_ERR_FORMAT; }
+  fill_info(m, name ? name : "device.csv", FX_ORDER_OVO);
   int rc = FX_OK;
+  unsigned* flag_dev = nullptr;
+  unsigned flag = 0;
   do {
     if (cudaMalloc(&m->rowptr_dev, sizeof(uint32_t) * (n + 1)) != cudaSuccess ||
         cudaMalloc(&m->col_dev, sizeof(uint32_t) * std::max<int64_t>(nnz, 1)) != cudaSuccess ||
-        cudaMalloc(&m->val_dev, sizeof(float) * std::max<int64_t>(nnz, 1)) != cudaSuccess) { rc = FX_ERR_NOMEM; break; }
+        cudaMalloc(&m->val_dev, sizeof(float) * std::max<int64_t>(nnz, 1)) != cudaSuccess ||
+        cudaMalloc(&m->vo_mp_dev, sizeof(int32_t) * std::max<int64_t>(n, 1)) != cudaSuccess ||
+        cudaMalloc(&flag_dev, sizeof(unsigned)) != cudaSuccess) { rc = FX_ERR_NOMEM; break; }
     if (cudaMemcpy(m->rowptr_dev, rowptr_dev, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToDevice) != cudaSuccess ||
         cudaMemcpy(m->col_dev, col_dev, sizeof(uint32_t) * nnz, cudaMemcpyDeviceToDevice) != cudaSuccess ||
-        cudaMemcpy(m->val_dev, val_dev, sizeof(float) * nnz, cudaMemcpyDeviceToDevice) != cudaSuccess) { rc = FX_ERR_CUDA; break; }
+        cudaMemcpy(m->val_dev, val_dev, sizeof(float) * nnz, cudaMemcpyDeviceToDevice) != cudaSuccess ||
+        cudaMemset(flag_dev, 0, sizeof(unsigned)) != cudaSuccess) { rc = FX_ERR_CUDA; break; }
+    if (n > 0) {
+      // the column checks of validate_csr (the builders index counters with col[e] and assume ascending columns) and the
+      // identity vo_mp of an unreordered matrix (fx_permute_rows / fx_unpermute_rows read it)
+      k_validate_cols<<<fx::ceil_div(n * 32, 256), 256>>>(m->rowptr_dev, m->col_dev, n, flag_dev);
+      k_iota<<<fx::ceil_div(n, 256), 256>>>(m->vo_mp_dev, n);
+      if (cudaMemcpy(&flag, flag_dev, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = FX_ERR_CUDA; break; }
+    }
   } while (0);
+  cudaFree(flag_dev);
   if (rc != FX_OK) { fx::set_error("fx_csr_from_device: device copy failed: %s", cudaGetErrorString(cudaGetLastError())); fx_matrix_free(m); return rc; }
+  if (flag) {
+    fx::set_error(flag & 1u ? "a column index is >= n (DataLoader.cu:58-59: the matrix must be square)"
+                            : "columns of a row are not strictly ascending (DataLoader.cu:97,272: unique, sorted dests)");
+    fx_matrix_free(m);
+    return FX_ERR_FORMAT;
+  }
+  m->vo_mp.resize(n);
+  std::iota(m->vo_mp.begin(), m->vo_mp.end(), 0);
   *out = m;
   return FX_OK;
 }

@@ -615,11 +615,8 @@ static int launch_one(PanelArgs a, const int* plist, int npan, const int2* wl, i
   // a uniform split (few panels, or FLEX_SPLIT) keeps the blockIdx mapping; otherwise the build's work list
   a.wl = (a.split == 1 && wl && nwl > 0 && !no_wl) ? wl : nullptr;
   dim3 grid(a.wl ? nwl : npan * a.split, kchunks);
-  static size_t set = 0;
-  if (smem > 48 * 1024 && smem > set) {
-    FX_CUDA(cudaFuncSetAttribute(k_spmm_rows<KC, WARPS, TILES, MINB, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    set = smem;
-  }
+  static SmemAttr attr;
+  if (int rc = attr.ensure(k_spmm_rows<KC, WARPS, TILES, MINB, G>, smem)) return rc;
   k_spmm_rows<KC, WARPS, TILES, MINB, G><<<grid, WARPS * 32, smem, s>>>(a, plist);
   FX_LAUNCH_CHECK();
   return FX_OK;
@@ -674,11 +671,8 @@ static int launch_aspt(const fx_tiles* t, const PanelArgs& a, int special_p, cud
 template <int N>
 static int launch_tc(const fxtc::TcArgs& ta, int ntc, cudaStream_t s) {
   const size_t smem = fxtc::tc_smem_bytes<N>(ta.W);
-  static size_t attr_set = 0;
-  if (smem > attr_set) {
-    FX_CUDA(cudaFuncSetAttribute(fxtc::k_spmm_tc<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = smem;
-  }
+  static SmemAttr attr;
+  if (int rc = attr.ensure(fxtc::k_spmm_tc<N>, smem)) return rc;
   dim3 grid(ntc, ceil_div(ta.width, N));
   fxtc::k_spmm_tc<N><<<grid, 256, smem, s>>>(ta);
   FX_LAUNCH_CHECK();
@@ -689,6 +683,8 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   if (width <= 0) width = k;
   const fx_aspt_dev& d = t->aspt;
   if (d.npanel == 0) return FX_OK;
+  // float4 offsets of B rows are 32-bit in the kernels (both entry points, fx_spmm and fx_spmm_host, come through here)
+  FX_REQUIRE((int64_t)t->mat->n * k / 4 < (1ll << 32), FX_ERR_UNSUPPORTED, "n*k too large for 32-bit float4 offsets");
   const int KC = pick_kc(width);
   PanelArgs a;
   a.tc_out = nullptr; a.tc_slot = nullptr; a.wl = nullptr;
@@ -712,6 +708,10 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   a.csr_e = d.csr_e_use; a.csr_ev = d.csr_ev_use;
   static const bool no_special = getenv("FLEX_NO_SPECIAL") != nullptr;
   const int special_p = no_special ? 0 : d.special_p;
+  // the 512-chunk partial sums live in a scratch sized for the build's k (fx_aspt_build.cu: special_cap * k floats): a
+  // wider call would write past it.  fx_spmm routes such calls to the CSR kernel; this is the backstop.
+  FX_REQUIRE((size_t)special_p * (size_t)k <= d.partial_cap_floats, FX_ERR_ARG,
+             "fx_spmm: k = %d is larger than the k = %d the tiles were built for", k, t->k);
   a.spec_off = special_p > 0 ? d.spec_off : nullptr;
   a.partial = d.partial;
   a.B = B; a.C = C;
@@ -719,8 +719,7 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   {  // fewer panels than SMs: several CTAs per panel.  Otherwise one CTA per work-list entry -- the row kernel
      // balances inside a panel by itself, and more CTAs only repeat its prologue (measured: flickr-shape 0.103 ms
      // unsplit vs 0.121 split in two; 1/8 Reddit-shape shards 0.136 / 0.129 / 0.141 / 0.146 ms for 1 / 2 / 3 / 4)
-    static int sm = 0;
-    if (!sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev); }
+    const int sm = sm_count_of_current_device();
     const char* e = getenv("FLEX_SPLIT");
     const int kch = ceil_div(width, KC);
     int sp = e ? atoi(e) : (d.npanel * kch >= sm ? 1 : ceil_div(2 * sm, d.npanel * kch));
@@ -739,9 +738,7 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
 
 int permute_rows(const int32_t* map, int64_t n, int k, const float* src, float* dst, bool scatter, cudaStream_t s) {
   if (n == 0) return FX_OK;
-  int dev = 0, sm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+  const int sm = sm_count_of_current_device();
   k_permute_rows<<<sm * 8, 256, 0, s>>>(map, n, k, src, dst, scatter);
   FX_LAUNCH_CHECK();
   return FX_OK;

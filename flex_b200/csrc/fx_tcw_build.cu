@@ -11,7 +11,7 @@
 //                         all threads at once                                -> win_cptr/code/val
 //   remainder           : every other nz as an ordinary CSR                  -> rest_rowptr/col/val
 // The remainder then goes through the ASpT builder unchanged (fx_aspt_build.cu), the window part is
-// multiplied by k_spmm_tc (fx_tc_kernel.cuh).  oracle/fx_oracle_tcw.c restates the selection rule
+// multiplied by k_spmm_tc (fx_tc_kernel.cuh).  oracle/tcw.py restates the selection rule
 // on the CPU; tests compare every array bit for bit.
 //
 // Selection rule (deterministic, all integer):  cnt_p[c] = nz of panel p in column c;  candidates =
@@ -398,11 +398,8 @@ int tcw_build(fx_tiles* t, cudaStream_t s) {
   FX_CUDA(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * 8, s));
   k_tcw_pad<<<ceil_div(a.nr + 1, 256), 256, 0, s>>>(m->rowptr_dev, t->row_begin, nloc, a.nr, ne, w.csr_v);
   FX_LAUNCH_CHECK();
-  static bool attr_set = false;
-  if (!attr_set) {
-    FX_CUDA(cudaFuncSetAttribute(k_tcw_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_CAP * sizeof(unsigned long long))));
-    attr_set = true;
-  }
+  static SmemAttr select_attr;
+  if (int rc = select_attr.ensure(k_tcw_select, CAND_CAP * sizeof(unsigned long long))) return rc;
   k_tcw_select<<<a.G, 512, CAND_CAP * sizeof(unsigned long long), s>>>(w.csr_v, col, a.npanel, (int)m->n, w.T, w.W, w.min_gain,
                                                                       w.chunk_cost, a.cnt_scratch, w.tc_cols, w.tc_ncol, w.win_len, w.chunk_len, w.stats);
   FX_LAUNCH_CHECK();
@@ -421,11 +418,8 @@ int tcw_build(fx_tiles* t, cudaStream_t s) {
   k_tcw_panels<<<1, 1024, 0, s>>>(w.tc_ncol, w.win_rowptr, a.npanel, a.nr, w.tc_panels, w.tc_slot, w.stats);
   FX_LAUNCH_CHECK();
   const size_t split_smem = sizeof(int) * (size_t)(w.W / 32) * BH;
-  static size_t split_set = 0;
-  if (split_smem > 48 * 1024 && split_smem > split_set) {
-    FX_CUDA(cudaFuncSetAttribute(k_tcw_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem));
-    split_set = split_smem;
-  }
+  static SmemAttr split_attr;
+  if (int rc = split_attr.ensure(k_tcw_split, split_smem)) return rc;
   k_tcw_split<<<a.G, 512, split_smem, s>>>(w.csr_v, col, val, w.win_rowptr, w.win_cptr, w.tc_cols, w.tc_ncol, a.npanel, (int)m->n,
                                            w.W, a.cnt_scratch, w.win_code, w.win_val, w.rest_col, w.rest_val);
   FX_LAUNCH_CHECK();

@@ -152,7 +152,9 @@ int fx_csr_load(const char *path, int k, fx_matrix **out);
 /* same from host arrays (no reference counterpart; the arrays DataLoader would have parsed) */
 int fx_csr_from_arrays(int64_t n, int64_t nnz, const uint32_t *rowptr, const uint32_t *col,
                        const float *val, int k, const char *name, fx_matrix **out);
-/* CSR already resident in HBM (arrays are copied device-to-device) */
+/* CSR already resident in HBM (arrays are copied device-to-device).  Same preconditions as the host loaders, checked by a
+ * device kernel: rowPtr monotone over [0,nnz], every column < n, columns strictly ascending within a row (unique and
+ * sorted, DataLoader.cu:97,272) -- FX_ERR_FORMAT otherwise.  vo_mp is the identity. */
 int fx_csr_from_device(int64_t n, int64_t nnz, const uint32_t *rowptr_dev, const uint32_t *col_dev,
                        const float *val_dev, int k, const char *name, fx_matrix **out);
 /* N2: Matrix Market coordinate file -> CSR, as data/SuiteSparse/mtx2csr.cc (mmio_allinone :57-222 +
@@ -208,7 +210,15 @@ void fx_tiles_free(fx_tiles *t); /* Mat::freeMatGPU* mat.cuh:184-220 */
 /* C[m x k] = A * B[n x k], row-major fp32, C fully overwritten (the reference pre-zeroes C and
  * accumulates with atomics: mat.cu:32-41, aspt/sspmm_128.cu:1147).  Asynchronous on `stream`
  * unless tElap_ms != NULL, in which case the call brackets the kernels with events, waits and
- * returns their elapsed time (flex.cu:5051-5068, aspt/sspmm_128.cu:1369-1380). */
+ * returns their elapsed time (flex.cu:5051-5068, aspt/sspmm_128.cu:1369-1380).
+ * - One SpMM in flight per handle: the 512-chunk partial sums, the window products and the timing events are scratch
+ *   of the fx_tiles handle (as the reference's device arrays are globals, aspt/sspmm_128.cu:76-90).  Two calls on
+ *   different streams need two handles (fx_build twice) or an event between them.
+ * - k may differ from the k the matrix was loaded with; a call with a LARGER k (or k % 4 != 0) on an ASpT /
+ *   tensor-window handle runs the raw-CSR kernel, because that scratch is sized for the build's k.
+ * - FX_FMT_TCW needs finite B: the dense window contraction multiplies the zeros of the A tile by every listed row of
+ *   B, so an Inf/NaN in such a row reaches all 128 rows of the panel (0 * Inf), where the reference's sparse semantics
+ *   (and every other format here) touch only the rows holding a nz in that column; tests/test_gpu_robustness.py. */
 int fx_spmm(const fx_tiles *t, const float *B_dev, float *C_dev, int k, void *stream,
             float *tElap_ms);
 /* Same with HOST buffers: copies B in, runs, copies C out (DataLoader.cu:216 + flex.cu:5690).
