@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--impl", default="flex_b200", choices=["flex_b200", "reference"])
     ap.add_argument("--allgather", action="store_true", help="also time the optional NCCL all-gather of C")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-amazon", action="store_true", help="skip the Amazon-shape k=128 sub-record (the north-star's scaling workload)")
     ap.add_argument("--cusparse", action="store_true", help="context number: torch.sparse (cuSPARSE) on the same GPU")
     return ap.parse_args()
 
@@ -51,24 +52,41 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernels_sha():
+    """Hash of the sources of the SpMM kernels and of the builders that lay out what they read."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("fx_spmm.cu", "fx_tc_kernel.cuh", "fx_aspt_build.cu", "fx_tcw_build.cu"):
+        with open(os.path.join(ROOT, "flex_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def measured_traffic(workload, k, fmt):
-    """DRAM bytes per step from the committed ncu capture of this workload (profiles/r1_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    key = f"{workload}:{k}" + ("" if fmt == "aspt" else f":{fmt}")
+    """DRAM bytes per step (dram__bytes_read.sum + dram__bytes_write.sum over the step's kernels) from the committed ncu
+    capture of this workload, profiles/r2_traffic.json -- reported only while the kernel sources are the ones captured."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
-        return json.load(open(p)).get(key, {}).get("bytes")
+        d = json.load(open(p))
+        if d.get("kernels_sha") != kernels_sha():
+            return None
+        return d.get("bytes", {}).get(f"{workload}:{k}:{fmt}")
     except Exception:
         return None
 
 
+FP32_FMA_PEAK = 148 * 128 * 2 * 1.965e9   # 74.4 TFLOP/s: 148 SMs x 128 lanes x 2 flop x 1965 MHz (BASELINE.md 1c)
+XBAR_PEAK = 148 * 64 * 1.93e9             # 18.3 TB/s: 64 B/clk per SM from L2, the rate k_spmm_special_cta sustains (ncu)
+
+
 def kernel_note(fmt, tcw):
-    tail = ("one step = all of them, timed together; the bound that binds is the L2->SM gather path (nnz*k*4 bytes), "
-            "see DESIGN.md section 5")
+    tail = ("one step = all of them, timed together (kernel_ms: CUDA events between them, this run); the bound that binds is "
+            "the L2->SM gather path (nnz*k*4 bytes), see DESIGN.md section 5")
     if fmt == "tcw" and tcw and tcw["ntc"]:
         share = 100.0 * tcw["win_nnz"] / max(1, tcw["win_nnz"] + tcw["rest_nnz"])
-        return ("k_spmm_rows (remainder nz, ~51 % of the step) + k_spmm_special_cta (512-nz chunks of long rows, ~28 %) + "
-                f"k_spmm_tc (tcgen05 3xTF32 over the panels' shared columns, {share:.0f} % of the nz, ~22 % of the step); " + tail)
-    return "k_spmm_rows (~75 % of the step) + k_spmm_special_cta (512-nz chunks of long rows); " + tail
+        return ("k_spmm_rows (remainder nz) + k_spmm_special_cta (512-nz chunks of long rows) + "
+                f"k_spmm_tc (tcgen05 3xTF32 over the panels' shared columns, {share:.0f} % of the nz); " + tail)
+    return "k_spmm_rows + k_spmm_special_cta (512-nz chunks of long rows); " + tail
 
 
 def algorithmic_bytes(n, nnz, k):
@@ -133,41 +151,30 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_baseline(rp, c, v, Bh, k, budget_s=12.0):
-    """The reference's CPU SpMM (aspt/sspmm_128.cu:1415-1422) restated in oracle/, all host
-    threads, on a bounded row-prefix sample of the same matrix."""
+def cpu_baseline(rp, c, v, Bh, k, budget_s=10.0):
+    """The reference's CPU SpMM (aspt/sspmm_128.cu:1415-1422) restated in oracle/ -- inner k-loop vectorised, rows over
+    all host cores -- on the WHOLE matrix, repeated for about `budget_s` seconds."""
     import numpy as np
     from oracle import orc
     orc.build()
-    n = len(rp) - 1
-    cores = orc.orc_num_threads() if hasattr(orc, "orc_num_threads") else orc.lib().orc_num_threads()
-    # probe on ~2% of the nz to size the sample
-    probe_rows = int(np.searchsorted(rp, rp[-1] * 0.02)) or 1
-    sub = rp[:probe_rows + 1].copy()
-    t0 = time.perf_counter()
-    orc.spmm_omp(sub, c[:sub[-1]], v[:sub[-1]], Bh)
-    t_probe = max(time.perf_counter() - t0, 1e-6)
-    rate = sub[-1] / t_probe
-    want_nnz = min(int(rp[-1]), int(rate * budget_s))
-    rows = int(np.searchsorted(rp, want_nnz, side="right")) - 1
-    rows = max(1, min(n, rows))
-    sub = rp[:rows + 1].copy()
-    out = np.empty((rows, k), np.float32)
-    nnz_s = int(sub[-1])
+    n, nnz = len(rp) - 1, int(rp[-1])
+    cores = int(orc.lib().orc_num_threads())
+    out = np.empty((n, k), np.float32)
+    orc.spmm_omp(rp, c, v, Bh, threads=cores, out=out)  # warm-up: thread pool, page faults of `out`
     passes, t0 = 0, time.perf_counter()
     while True:
-        orc.spmm_omp(sub, c[:nnz_s], v[:nnz_s], Bh, out=out)
+        orc.spmm_omp(rp, c, v, Bh, threads=cores, out=out)
         passes += 1
         dt = time.perf_counter() - t0
         if dt >= budget_s or passes >= 1000:
             break
-    return {"value": 2.0 * nnz_s * k * passes / dt / 1e9, "unit": "GFLOP/s", "cores": int(cores), "kind": "port",
-            "sample": f"rows [0,{rows}) of the workload ({nnz_s} nz, {100.0 * nnz_s / int(rp[-1]):.1f}% of nnz), "
-                      f"{passes} passes, {dt:.2f} s, OpenMP row-parallel restatement of aspt/sspmm_128.cu:1415-1422"}
+    return {"value": 2.0 * nnz * k * passes / dt / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port",
+            "sample": f"the whole workload ({nnz} nz) x {passes} passes after one warm-up pass, {dt:.2f} s; OpenMP row-parallel, "
+                      f"vectorised (AVX-512/AVX2 clones) restatement of aspt/sspmm_128.cu:1415-1422, bit-identical to the scalar loop"}
 
 
 def run_reference(args, k):
-    """--impl reference: the reference's own CPU SpMM (oracle port) on the host cores, rank 0 only."""
+    """--impl reference: the reference's own CPU SpMM (oracle port, all host cores) over the WHOLE matrix per step; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -179,33 +186,23 @@ def run_reference(args, k):
     n, nnz = len(rp) - 1, len(c)
     from flex_b200 import synth
     Bh = synth.dense_B(n, k).numpy()
-    cores = orc.lib().orc_num_threads()
-    # bounded sample: a row prefix that takes ~1.5 s per step
-    probe_rows = int(np.searchsorted(rp, rp[-1] * 0.02)) or 1
-    sub = rp[:probe_rows + 1].copy()
-    t0 = time.perf_counter()
-    orc.spmm_omp(sub, c[:sub[-1]], v[:sub[-1]], Bh)
-    rate = sub[-1] / max(time.perf_counter() - t0, 1e-6)
-    budget = min(1.5, 150.0 / max(1, args.steps + args.warmup))
-    rows = max(1, min(n, int(np.searchsorted(rp, min(nnz, int(rate * budget)), side="right")) - 1))
-    sub = rp[:rows + 1].copy()
-    nnz_s = int(sub[-1])
-    out = np.empty((rows, k), np.float32)
-    for _ in range(args.warmup):
-        orc.spmm_omp(sub, c[:nnz_s], v[:nnz_s], Bh, out=out)
+    cores = int(orc.lib().orc_num_threads())  # omp_get_num_procs(): torchrun's OMP_NUM_THREADS=1 does not apply
+    out = np.empty((n, k), np.float32)
+    for _ in range(max(1, args.warmup)):
+        orc.spmm_omp(rp, c, v, Bh, threads=cores, out=out)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.spmm_omp(sub, c[:nnz_s], v[:nnz_s], Bh, out=out)
+        orc.spmm_omp(rp, c, v, Bh, threads=cores, out=out)
     dt = (time.perf_counter() - t0) / max(1, args.steps)
-    val = 2.0 * nnz_s * k / dt / 1e9
-    sample = (f"rows [0,{rows}) of the workload ({nnz_s} nz, {100.0 * nnz_s / nnz:.1f}% of nnz) per step; "
-              f"OpenMP restatement of the reference CPU SpMM aspt/sspmm_128.cu:1415-1422 (the reference embeds its "
-              f"CPU loop in a CUDA main(), so it cannot be timed alone)")
+    val = 2.0 * nnz * k / dt / 1e9
+    sample = (f"the whole workload ({nnz} nz) per step on {cores} host threads; OpenMP row-parallel, vectorised restatement of the "
+              f"reference CPU SpMM aspt/sspmm_128.cu:1415-1422 (the reference embeds its CPU loop in a CUDA main(), so it cannot be "
+              f"timed alone; built -O3 as aspt/h100_compile_GPU_SpMM_ASpT.sh:7 does)")
     line = {"impl": "reference", "metric": "SpMM GFLOP/s (2*nnz*k/tElap)", "value": val, "unit": "GFLOP/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, k, n, nnz),
-            "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": int(cores), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -216,10 +213,9 @@ def workload_config(args, k, n, nnz):
             "k": k, "format": args.fmt, "order": args.order, "shuffled_ids": bool(args.shuffle),
             "l2_policy": "inputs larger than L2 (A+B+C bytes > 126 MB)" if algorithmic_bytes(n, nnz, k) > 126e6
             else "whole problem fits L2: L2 flushed by a 256 MB write between timed steps",
-            "arithmetic": ("fp32 mul+add on the host cores (the reference's CPU SpMM)" if args.impl == "reference" else
-                           "fp32 FMA for the remainder; tensor windows on tcgen05 with the 3xTF32 split (hi*hi + hi*lo + lo*hi), "
-                           "fp32 accumulate" if args.fmt == "tcw" else "fp32 FMA"),
-            "parallelism": f"row-panel shards x{args.gpus}, B replicated"}
+            # the same strings in both arms (the driver compares the configs): what differs is said per arm
+            "arithmetic": "fp32 (reference arm: mul+add on the host cores; flex_b200 arm: FMA, tensor windows on tcgen05 with the 3xTF32 split)",
+            "parallelism": "row-panel shards over the GPUs of the run, B replicated (reference arm: one host, all cores)"}
 
 
 def e2e_sharded(dist, mat, Bh, Ch, n, k, lo, hi, rank, world, dev, steps, sync_all):
@@ -273,6 +269,89 @@ def e2e_sharded(dist, mat, Bh, Ch, n, k, lo, hi, rank, world, dev, steps, sync_a
         return None, None, "sharded-input path failed: %r" % (ex,)
 
 
+def timed_steps(step, steps, warmup, small, flush, dist, dev):
+    """W untimed + exactly K timed steps bracketed by barrier + synchronize; device time by CUDA events on the launching
+    stream, max over ranks.  Returns ms per step."""
+    import torch
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 3)):
+        step()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if small:  # problem fits in L2: flush between steps and sum per-step event times
+        ms = 0.0
+        for _ in range(steps):
+            flush.fill_(1.0)
+            e0.record(); step(); e1.record()
+            e1.synchronize()
+            ms += e0.elapsed_time(e1)
+    else:
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+    sync_all()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item() / steps
+
+
+def build_workload(fx, args, workload, k, dev, world, rank, order="ovo", shuffle=False, fmt=None):
+    """Synthetic graph on the device -> DataLoader -> this rank's row-panel shard built in the requested format."""
+    import numpy as np
+    import torch
+    from flex_b200.shard import panel_shards
+    rp, c, v = load_workload(workload, k, dev, shuffle)
+    n, nnz = rp.numel() - 1, c.numel()
+    rp_host = rp.cpu().numpy()
+    rp32, c32 = rp.to(torch.int32), c.to(torch.int32)
+    if order != "ovo":
+        dl0 = fx.DataLoader.from_arrays(rp_host.astype(np.uint32), c.cpu().numpy().astype(np.uint32), v.cpu().numpy(), k, workload + ".csv")
+        dl = dl0.reorder({"deg": fx.FX_ORDER_DEG, "rcm": fx.FX_ORDER_RCM, "gor": fx.FX_ORDER_GOR, "dfs": fx.FX_ORDER_DFS, "rbt": fx.FX_ORDER_RBT}[order])
+        rp_host = dl.rowPtr.astype(np.int64)
+    else:
+        dl = fx.DataLoader.from_device(n, nnz, rp32.data_ptr(), c32.data_ptr(), v.data_ptr(), k, workload + ".csv")
+    shards = panel_shards(rp_host, world)
+    lo, hi = shards[rank]
+    mat = fx.Mat(dl, fmt=fmt or args.fmt, row_begin=lo, row_end=hi, tc_threshold=args.tc_threshold, tc_width=args.tc_width,
+                 tc_min_gain=args.tc_min_gain, tc_chunk_cost=args.tc_chunk_cost, tc_min_total=args.tc_min_total)
+    return dict(rp=rp, c=c, v=v, rp32=rp32, c32=c32, n=n, nnz=nnz, rp_host=rp_host, dl=dl, shards=shards, lo=lo, hi=hi, mat=mat)
+
+
+def amazon_record(fx, args, dev, world, rank, dist):
+    """The north-star's scaling workload next to the headline: Amazon-shape k=128, this run's GPUs, 5 timed steps after 3."""
+    import torch
+    from flex_b200 import synth
+    k = 128
+    w = build_workload(fx, args, "amazon", k, dev, world, rank)
+    mat, n, nnz, lo, hi = w["mat"], w["n"], w["nnz"], w["lo"], w["hi"]
+    tpre = min([mat.tPre_ms] + [mat.rebuild() for _ in range(2)])
+    B = synth.dense_B(n, k, device=dev)
+    Cd = torch.empty((hi - lo, k), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ms = timed_steps(lambda: mat.spmm(B.data_ptr(), Cd.data_ptr(), k, stream=stream), 5, 3, False, None, dist, dev)
+    loc = torch.tensor([int(w["rp_host"][hi] - w["rp_host"][lo])], dtype=torch.int64, device=dev)
+    per_rank = [loc.clone() for _ in range(world)]
+    if dist is not None:
+        dist.all_gather(per_rank, loc)
+    tcw = mat.tcw_info() if args.fmt == "tcw" else None
+    rec = {"workload": "amazon-shape", "n": n, "nnz": nnz, "k": k, "steps": 5, "warmup": 3, "ms_per_step": ms,
+           "value": 2.0 * nnz * k / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "scaling": "strong",
+           "hbm_frac": algorithmic_bytes(n, nnz, k) / (ms * 1e-3) / 1e9 / peaks()[0],
+           "tPre_ms_rank0": tpre, "tensor_windows_rank0": tcw, "nnz_per_rank": [int(x.item()) for x in per_rank]}
+    mat.free()
+    return rec
+
+
 def main():
     args = parse()
     k = args.k or DEFAULT_K.get(args.workload, 128)
@@ -297,23 +376,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    rp, c, v = load_workload(args.workload, k, dev, args.shuffle)
-    n, nnz = rp.numel() - 1, c.numel()
-    rp_host = rp.cpu().numpy()
-    rp32, c32 = rp.to(torch.int32), c.to(torch.int32)
-    need_host = args.order != "ovo"
-    if need_host:
-        dl0 = fx.DataLoader.from_arrays(rp_host.astype(np.uint32), c.cpu().numpy().astype(np.uint32), v.cpu().numpy(), k,
-                                        args.workload + ".csv")
-        dl = dl0.reorder({"deg": fx.FX_ORDER_DEG, "rcm": fx.FX_ORDER_RCM, "gor": fx.FX_ORDER_GOR, "dfs": fx.FX_ORDER_DFS, "rbt": fx.FX_ORDER_RBT}[args.order])
-        rp_host = dl.rowPtr.astype(np.int64)
-    else:
-        dl = fx.DataLoader.from_device(n, nnz, rp32.data_ptr(), c32.data_ptr(), v.data_ptr(), k, args.workload + ".csv")
-    from flex_b200.shard import panel_shards
-    shards = panel_shards(rp_host, world)
-    lo, hi = shards[rank]
-    mat = fx.Mat(dl, fmt=args.fmt, row_begin=lo, row_end=hi, tc_threshold=args.tc_threshold, tc_width=args.tc_width,
-                 tc_min_gain=args.tc_min_gain, tc_chunk_cost=args.tc_chunk_cost, tc_min_total=args.tc_min_total)
+    w = build_workload(fx, args, args.workload, k, dev, world, rank, args.order, args.shuffle)
+    rp, c, v, n, nnz, rp_host, lo, hi, mat, shards = (w[x] for x in ("rp", "c", "v", "n", "nnz", "rp_host", "lo", "hi", "mat", "shards"))
     tpre = [mat.tPre_ms] + [mat.rebuild() for _ in range(3)]
     tcw = mat.tcw_info() if args.fmt == "tcw" else None
     B = synth.dense_B(n, k, device=dev)
@@ -331,31 +395,11 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sync_all()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = fx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if small:
-        # problem fits in L2: flush between steps and sum per-step event times
-        tot = 0.0
-        for _ in range(args.steps):
-            flush.fill_(1.0)
-            e0.record(); step(); e1.record()
-            e1.synchronize()
-            tot += e0.elapsed_time(e1)
-        ms = tot
-    else:
-        e0.record()
-        for _ in range(args.steps):
-            step()
-        e1.record()
-        e1.synchronize()
-        ms = e0.elapsed_time(e1)
-    launches = fx.launch_count() - l0
-    sync_all()
+    ms_per_step = timed_steps(step, args.steps, args.warmup, small, flush, dist, dev)
+    launches = (fx.launch_count() - l0) * args.steps // (args.steps + max(args.warmup, 3))  # the timed steps' share
     # keep the device busy long enough for the clock sampler to see the kernel under load
     t_end = time.time() + 0.5
     while len(sampler.samples) < 50 and time.time() < t_end:
@@ -364,27 +408,34 @@ def main():
         torch.cuda.synchronize()
     sampler.stop_flag = True
     sampler.join()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = t.item() / args.steps
 
-    # end to end through the public call with HOST buffers (pinned): H2D B, kernels, D2H C
+    # per-kernel times of the same step, measured in THIS run with events between the kernels (5 steps)
+    kernel_ms = None
+    if args.fmt in ("tcw", "aspt") and k % 4 == 0:
+        acc = {}
+        for _ in range(5):
+            if small:
+                flush.fill_(1.0)
+            for name, t in mat.kernel_times(B.data_ptr(), Cd.data_ptr(), k, stream=stream).items():
+                acc[name] = acc.get(name, 0.0) + t / 5
+        kernel_ms = acc
+
+    # end to end through the public call with HOST buffers (pinned): H2D B, kernels, D2H C -- wall clock around the call
     Bh = torch.empty((n, k), dtype=torch.float32).pin_memory()
     Bh.copy_(B)
     Ch = torch.empty((hi - lo, k), dtype=torch.float32).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
     mat.spmm_host(Bh.numpy(), out=Ch.numpy())
     sync_all()
-    t0 = time.perf_counter()
-    dev_ms = 0.0
+    dev_ms, t0 = 0.0, time.perf_counter()
     for _ in range(e2e_steps):
-        mat.spmm_host(Bh.numpy(), out=Ch.numpy())
+        mat.spmm_host(Bh.numpy(), out=Ch.numpy())  # returns when C is in host memory
         dev_ms += mat.last_total_ms
-    e2e_ms = torch.tensor([dev_ms / e2e_steps], dtype=torch.float64, device=dev)
+    wall_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_t = torch.tensor([wall_ms, dev_ms / e2e_steps], dtype=torch.float64, device=dev)
     if dist is not None:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms = e2e_ms.item()
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms, e2e_dev_ms = e2e_t[0].item(), e2e_t[1].item()
     e2e_h2d, e2e_note, e2e_replicated_ms = int(4 * n * k), None, None
     if dist is not None:
         sh_ms, sh_h2d, e2e_note = e2e_sharded(dist, mat, Bh, Ch, n, k, lo, hi, rank, world, dev, e2e_steps, sync_all)
@@ -405,12 +456,46 @@ def main():
         dist.all_reduce(ag, op=dist.ReduceOp.MAX)
         ag_ms = ag.item()
 
+    cusparse = None
+    if args.cusparse and rank == 0:
+        # context only, same protocol as the timed region (L2 flushed between steps when it fits)
+        A = torch.sparse_csr_tensor(rp, c, v, size=(n, n))
+        for _ in range(3):
+            torch.sparse.mm(A, B)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for _ in range(10):
+            if small:
+                flush.fill_(1.0)
+            c0.record()
+            torch.sparse.mm(A, B)
+            c1.record(); c1.synchronize()
+            tot += c0.elapsed_time(c1)
+        cusparse = 2.0 * nnz * k / (tot / 10 * 1e-3) / 1e9
+        del A
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(rp_host.astype(np.uint32), w["c32"].cpu().numpy().view(np.uint32), v.cpu().numpy(), Bh.numpy(), k)
+
+    loc_nnz = int(rp_host[hi] - rp_host[lo])
+    mat.free()
+    del w, rp, c, v, B, Cd, Bh, Ch, flush, mat
+    torch.cuda.empty_cache()
+
+    amazon = None
+    if args.workload != "amazon" and not args.no_amazon:
+        try:
+            amazon = amazon_record(fx, args, dev, world, rank, dist)
+        except Exception as ex:  # the headline line must survive (e.g. out of memory on a shared box)
+            amazon = {"workload": "amazon-shape", "failed": repr(ex)[:200]}
+
     if rank == 0:
         flops = 2.0 * nnz * k
         value = flops / (ms_per_step * 1e-3) / 1e9
         peak, peak_src = peaks()
-        # roofline for the dominant kernel: every rank streams its share of A and C plus (at most) all of B
-        loc_nnz = int(rp_host[hi] - rp_host[lo])
+        # roofline of the step: every rank streams its share of A and C plus (at most) all of B
         abytes = 4 * (hi - lo + 1) + 8 * loc_nnz + 4 * n * k + 4 * (hi - lo) * k
         achieved = abytes / (ms_per_step * 1e-3) / 1e9
         line = {
@@ -425,24 +510,29 @@ def main():
                          "traffic": measured_traffic(args.workload, k, args.fmt) if (world == 1 and args.order == "ovo" and not args.shuffle) else None,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes,
-                         "kernel": kernel_note(args.fmt, tcw)},
+                         "kernel": kernel_note(args.fmt, tcw),
+                         "kernel_ms": kernel_ms},
             "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
+                    "device_ms_per_step": e2e_dev_ms, "timer": "host wall clock around the call (pinned host buffers in, C back in host memory)",
                     "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": int(4 * (hi - lo) * k)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
         try:
-            # second view of the same step: the bytes the SMs must pull through the L2->SM crossbar (the path that binds,
-            # DESIGN.md section 5) -- one B row per gathered nz, one per listed window column, tc_out out and back, A, C --
-            # against the rate the 512-chunk kernel sustains on this access pattern (18.3 TB/s, ncu:
-            # profiles/r1_ncu_tcw_reddit_k128.md); hits in L1 make the real transfer smaller, so this is an upper estimate
+            # The roofs this step can be held against: HBM (algorithmic bytes), fp32 FMA, and the bytes
+            # the SMs must pull through the L2->SM crossbar -- one B row per gathered nz and per listed window column, tc_out
+            # out and back, A, C -- at 64 B/clk per SM.  `restated` = the largest of the three lower bounds over the step time.
             g_nz = tcw["rest_nnz"] if (tcw and tcw.get("ntc")) else loc_nnz
             g_cols = tcw["listed_columns"] if (tcw and tcw.get("ntc")) else 0
             g_tc = 2 * tcw["ntc"] * 128 * k * 4 if (tcw and tcw.get("ntc")) else 0
             g_bytes = 4 * k * (g_nz + g_cols) + g_tc + 8 * loc_nnz + 4 * (hi - lo) * k
-            line["roofline"]["gather_path"] = {"bytes": int(g_bytes), "achieved": g_bytes / (ms_per_step * 1e-3) / 1e12,
-                                               "ceiling": 18.3, "unit": "TB/s",
-                                               "frac": g_bytes / (ms_per_step * 1e-3) / 1e12 / 18.3}
+            t_step = ms_per_step * 1e-3
+            bounds = {"hbm": abytes / (peak * 1e9), "fp32_fma": (2.0 * loc_nnz * k) / FP32_FMA_PEAK, "xbar": g_bytes / XBAR_PEAK}
+            binding = max(bounds, key=bounds.get)
+            line["roofline"]["gather_path"] = {"bytes": int(g_bytes), "achieved": g_bytes / t_step / 1e12,
+                                               "ceiling": XBAR_PEAK / 1e12, "unit": "TB/s", "frac": g_bytes / t_step / XBAR_PEAK}
+            line["roofline"]["restated"] = {"lower_bounds_us": {kk: vv * 1e6 for kk, vv in bounds.items()}, "binding": binding,
+                                            "frac": bounds[binding] / t_step}
         except Exception:
             pass
         if e2e_note is not None:
@@ -451,25 +541,12 @@ def main():
             line["e2e"]["replicated_ms"] = e2e_replicated_ms
         if ag_ms is not None:
             line["allgather_ms"] = ag_ms
-        if args.cusparse:
-            # context only, same protocol as the timed region (L2 flushed between steps when it fits)
-            A = torch.sparse_csr_tensor(rp, c, v, size=(n, n))
-            for _ in range(3):
-                torch.sparse.mm(A, B)
-            torch.cuda.synchronize()
-            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            tot = 0.0
-            for _ in range(10):
-                if small:
-                    flush.fill_(1.0)
-                c0.record()
-                torch.sparse.mm(A, B)
-                c1.record(); c1.synchronize()
-                tot += c0.elapsed_time(c1)
-            line["cusparse_context_gflops"] = flops / (tot / 10 * 1e-3) / 1e9
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(rp_host.astype(np.uint32), c32.cpu().numpy().view(np.uint32),
-                                                v.cpu().numpy(), Bh.numpy(), k)
+        if cusparse is not None:
+            line["cusparse_context_gflops"] = cusparse
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if amazon is not None:
+            line["amazon"] = amazon
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

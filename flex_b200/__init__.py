@@ -115,7 +115,7 @@ ABI_SYMBOLS = [
     "fx_csr_from_arrays", "fx_csr_from_device", "fx_mtx_load", "fx_csr_write_csv", "fx_csr_save_bin", "fx_csr_load_bin", "fx_matrix_get_info", "fx_matrix_host_csr",
     "fx_matrix_device_csr", "fx_matrix_free", "fx_rand_B", "fx_reorder", "fx_reorder_with_rank",
     "fx_permutation", "fx_permute_rows", "fx_unpermute_rows", "fx_build", "fx_rebuild",
-    "fx_tiles_export_aspt", "fx_tiles_export_tile", "fx_tiles_export_seg", "fx_tiles_export_pillar", "fx_tiles_export_tcw", "fx_tiles_tcw_info", "fx_tiles_free", "fx_spmm", "fx_spmm_host", "fx_check",
+    "fx_tiles_export_aspt", "fx_tiles_export_tile", "fx_tiles_export_seg", "fx_tiles_export_pillar", "fx_tiles_export_tcw", "fx_tiles_tcw_info", "fx_tiles_free", "fx_spmm", "fx_spmm_kernel_times", "fx_spmm_host", "fx_check",
 ]
 
 
@@ -161,6 +161,7 @@ def lib():
     L.fx_tiles_free.argtypes = [vp]
     L.fx_tiles_free.restype = None
     L.fx_spmm.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(C.c_float)]
+    L.fx_spmm_kernel_times.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(C.c_float)]
     L.fx_spmm_host.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.fx_check.argtypes = [vp, vp, C.c_int64, C.c_int, vp, C.POINTER(Report)]
     _lib = L
@@ -428,6 +429,13 @@ class Mat:
         t = C.c_float()
         _ck(lib().fx_spmm(self._h, B_ptr, C_ptr, int(k), stream, C.byref(t) if timed else None))
         return t.value if timed else None
+
+    def kernel_times(self, B_ptr, C_ptr, k, stream=None):
+        """One SpMM with events between its kernels: dict of ms for the tensor-window kernel, the 512-chunk kernel of
+        long rows, the row kernel and the whole step."""
+        ms = (C.c_float * 4)()
+        _ck(lib().fx_spmm_kernel_times(self._h, B_ptr, C_ptr, int(k), stream, ms))
+        return {"k_spmm_tc": ms[0], "k_spmm_special_cta": ms[1], "k_spmm_rows": ms[2], "step": ms[3]}
 
     def spmm_host(self, B, out=None):
         """Host buffers in, host buffer out (H2D + kernels + D2H)."""

@@ -202,6 +202,13 @@ extern "C" int fx_spmm(const fx_tiles* t, const float* B_dev, float* C_dev, int 
   return FX_OK;
 }
 
+extern "C" int fx_spmm_kernel_times(const fx_tiles* t, const float* B_dev, float* C_dev, int k, void* stream, float ms[4]) {
+  FX_REQUIRE(t && B_dev && C_dev && k > 0 && ms, FX_ERR_ARG, "fx_spmm_kernel_times: bad argument");
+  FX_REQUIRE((t->format == FX_FMT_ASPT || t->format == FX_FMT_TCW) && k % 4 == 0 && k <= t->k, FX_ERR_UNSUPPORTED,
+             "fx_spmm_kernel_times: ASpT / tensor-window handles, k %% 4 == 0 and k <= the build's k");
+  return fx::spmm_aspt_times(t, B_dev, C_dev, k, static_cast<cudaStream_t>(stream), ms);
+}
+
 extern "C" int fx_spmm_host(const fx_tiles* tc, const float* B_host, float* C_host, int k, float* total_ms,
                             float* tElap_ms) {
   FX_REQUIRE(tc && B_host && C_host && k > 0, FX_ERR_ARG, "fx_spmm_host: bad argument");

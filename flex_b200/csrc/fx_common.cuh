@@ -228,6 +228,7 @@ int spmm_csr(const uint32_t* rowptr, const uint32_t* col, const float* val, int6
              float* C, int k, cudaStream_t s);
 // width > 0: compute only `width` feature columns starting at the B / C pointers (row stride stays k)
 int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s, int width = 0);
+int spmm_aspt_times(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s, float ms[4]);
 int permute_rows(const int32_t* map, int64_t n, int k, const float* src, float* dst, bool scatter,
                  cudaStream_t s);
 }  // namespace fx

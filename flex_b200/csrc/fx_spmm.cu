@@ -641,6 +641,13 @@ static int launch_panels(const fx_aspt_dev& d, const PanelArgs& a, int kchunks, 
   return FX_OK;
 }
 
+// fx_spmm_kernel_times: events recorded between the kernels of one SpMM (null outside that call)
+static thread_local cudaEvent_t* g_prof = nullptr;
+static int prof_mark(int i, cudaStream_t s) {
+  if (g_prof) FX_CUDA(cudaEventRecord(g_prof[i], s));
+  return FX_OK;
+}
+
 template <int KC>
 static int launch_aspt(const fx_tiles* t, const PanelArgs& a, int special_p, cudaStream_t s) {
   const fx_aspt_dev& d = t->aspt;
@@ -657,6 +664,7 @@ static int launch_aspt(const fx_tiles* t, const PanelArgs& a, int special_p, cud
     }
     FX_LAUNCH_CHECK();
   }
+  if (int rc = prof_mark(2, s)) return rc;
   // Measured on Reddit-shape k=128 (ms per SpMM): 0.569 default; 0.576 <16,2,16>; 0.577 <16,2,8>; 0.582 <8,6,8>; fewer, fatter
   // warps lose (<8,4,16> 0.589, <8,3,12> 0.617, <8,3,16> 0.631, <8,2,16> at 101 registers 0.689): the per-row latency chain
   // (grab, metadata, B rounds, window product, store) is covered by warps, not by loads in flight per warp
@@ -693,6 +701,7 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   static const int team_row = getenv("FLEX_TEAM_ROW") ? atoi(getenv("FLEX_TEAM_ROW")) : 0;
   a.team_row = team_row;
   a.tiles_ok = (int64_t)t->mat->n * k / 4 < (1ll << 31);
+  if (int rc = prof_mark(0, s)) return rc;
   if (t->format == FX_FMT_TCW && t->tcw.ntc > 0) {  // tensor windows first; the panel kernel adds them in
     const fx_tcw_dev& w = t->tcw;
     fxtc::TcArgs ta;
@@ -704,6 +713,7 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
     if (rc != FX_OK) return rc;
     a.tc_out = w.tc_out; a.tc_slot = w.tc_slot;
   }
+  if (int rc = prof_mark(1, s)) return rc;
   a.mcsr_cnt = d.mcsr_cnt; a.mcsr_e = d.mcsr_e_use; a.mcsr_list = d.mcsr_list;
   a.csr_e = d.csr_e_use; a.csr_ev = d.csr_ev_use;
   static const bool no_special = getenv("FLEX_NO_SPECIAL") != nullptr;
@@ -731,9 +741,29 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   while (ts > 1 && ts * tile_bytes > 160 * 1024) --ts;  // leave room for the per-worker buffers
   a.TS = ts > 0 ? ts : 1;
   if (d.max_tp == 0) a.TS = 0;
-  if (KC == 32) return launch_aspt<32>(t, a, special_p, s);
-  if (KC == 64) return launch_aspt<64>(t, a, special_p, s);
-  return launch_aspt<128>(t, a, special_p, s);
+  const int rc = KC == 32 ? launch_aspt<32>(t, a, special_p, s) : (KC == 64 ? launch_aspt<64>(t, a, special_p, s) : launch_aspt<128>(t, a, special_p, s));
+  if (rc != FX_OK) return rc;
+  return prof_mark(3, s);
+}
+
+// One SpMM with events between its kernels: ms[0] = tensor-window kernel, ms[1] = 512-chunk kernel, ms[2] = row kernel,
+// ms[3] = the whole step (ASpT / tensor-window formats; a kernel that does not run reports 0).
+int spmm_aspt_times(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s, float ms[4]) {
+  cudaEvent_t ev[4] = {};
+  for (int i = 0; i < 4; ++i) FX_CUDA(cudaEventCreate(&ev[i]));
+  g_prof = ev;
+  const int rc = spmm_aspt(t, B, C, k, s);
+  g_prof = nullptr;
+  int out = rc;
+  if (rc == FX_OK) {
+    if (cudaEventSynchronize(ev[3]) != cudaSuccess) out = FX_ERR_CUDA;
+    for (int i = 0; i < 3 && out == FX_OK; ++i)
+      if (cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]) != cudaSuccess) out = FX_ERR_CUDA;
+    if (out == FX_OK && cudaEventElapsedTime(&ms[3], ev[0], ev[3]) != cudaSuccess) out = FX_ERR_CUDA;
+  }
+  for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+  if (out == FX_ERR_CUDA && rc == FX_OK) set_error("fx_spmm_kernel_times: event timing failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return out;
 }
 
 int permute_rows(const int32_t* map, int64_t n, int k, const float* src, float* dst, bool scatter, cudaStream_t s) {

@@ -221,6 +221,11 @@ void fx_tiles_free(fx_tiles *t); /* Mat::freeMatGPU* mat.cuh:184-220 */
  *   (and every other format here) touch only the rows holding a nz in that column; tests/test_gpu_robustness.py. */
 int fx_spmm(const fx_tiles *t, const float *B_dev, float *C_dev, int k, void *stream,
             float *tElap_ms);
+/* The same SpMM with events between its kernels (the reference times its kernel section as a whole,
+ * aspt/sspmm_128.cu:1369-1380; this is what the per-kernel NPerf counters of flex.cu:4583-4656 are for):
+ * ms[0] = tensor-window kernel, ms[1] = 512-chunk kernel of long rows, ms[2] = row kernel, ms[3] = the step.
+ * ASpT / tensor-window handles only; waits for the step to finish. */
+int fx_spmm_kernel_times(const fx_tiles *t, const float *B_dev, float *C_dev, int k, void *stream, float ms[4]);
 /* Same with HOST buffers: copies B in, runs, copies C out (DataLoader.cu:216 + flex.cu:5690).
  * Uses an internal pinned staging area if the buffers are pageable. */
 int fx_spmm_host(const fx_tiles *t, const float *B_host, float *C_host, int k, float *total_ms,

@@ -173,26 +173,36 @@ void orc_spmm_ref(int64_t n, const uint32_t *rowptr, const uint32_t *col, const 
     }
 }
 
-/* identical per-row order; rows distributed over threads; the product is rounded
- * to fp32 before the add exactly as above (no FMA contraction). */
+/* identical per-row order; rows distributed over threads; the product is rounded to fp32 before the
+ * add exactly as above (no FMA contraction: -ffp-contract=off), so the result is bit-identical to
+ * orc_spmm_ref.  This is the CPU BASELINE of bench.py, built the way BASELINE.md section 3 prescribes and
+ * the reference itself compiles its loop (-O3, aspt/h100_compile_GPU_SpMM_ASpT.sh:7): the inner k-loop is
+ * vectorised.  The shared object is built in one container and runs on another box, so instead of
+ * -march=native the row kernel is cloned for AVX-512 / AVX2 / baseline x86-64 and picked at load time. */
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define ORC_VEC __attribute__((target_clones("avx512f", "avx2", "default")))
+#else
+#define ORC_VEC
+#endif
+ORC_VEC static void orc_row_accumulate(const uint32_t *restrict col, const float *restrict val, uint32_t lo, uint32_t hi,
+                                       const float *restrict B, int k, float *restrict c) {
+  for (int j = 0; j < k; ++j) c[j] = 0.0f;
+  for (uint32_t e = lo; e < hi; ++e) {
+    const float *restrict b = B + (int64_t)col[e] * k;
+    const float v = val[e];
+    for (int j = 0; j < k; ++j) c[j] = c[j] + (float)(b[j] * v);
+  }
+}
+
 int orc_spmm_omp(int64_t n, const uint32_t *rowptr, const uint32_t *col, const float *val,
                  const float *B, int k, float *C, int threads) {
   int used = 1;
 #ifdef _OPENMP
-  if (threads <= 0) threads = omp_get_max_threads();
+  if (threads <= 0) threads = omp_get_num_procs(); /* NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 */
   used = threads;
-#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(threads)
 #endif
-  for (int64_t r = 0; r < n; ++r) {
-    float *c = C + r * k;
-    for (int j = 0; j < k; ++j) c[j] = 0.0f;
-    for (uint32_t e = rowptr[r]; e < rowptr[r + 1]; ++e) {
-      const float *b = B + (int64_t)col[e] * k;
-      float v = val[e];
-#pragma GCC unroll 1
-      for (int j = 0; j < k; ++j) c[j] = c[j] + (float)(b[j] * v);
-    }
-  }
+  for (int64_t r = 0; r < n; ++r) orc_row_accumulate(col, val, rowptr[r], rowptr[r + 1], B, k, C + r * k);
   return used;
 }
 
@@ -217,18 +227,11 @@ void orc_spmm_f64(int64_t n, const uint32_t *rowptr, const uint32_t *col, const 
 void orc_spmm_rows(const int64_t *rows, int64_t nrows, const uint32_t *rowptr, const uint32_t *col,
                    const float *val, const float *B, int k, float *C /* nrows*k */) {
 #ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 16)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(omp_get_num_procs())
 #endif
   for (int64_t i = 0; i < nrows; ++i) {
     int64_t r = rows[i];
-    float *c = C + i * k;
-    for (int j = 0; j < k; ++j) c[j] = 0.0f;
-    for (uint32_t e = rowptr[r]; e < rowptr[r + 1]; ++e) {
-      const float *b = B + (int64_t)col[e] * k;
-      float v = val[e];
-#pragma GCC unroll 1
-      for (int j = 0; j < k; ++j) c[j] = c[j] + (float)(b[j] * v);
-    }
+    orc_row_accumulate(col, val, rowptr[r], rowptr[r + 1], B, k, C + i * k);
   }
 }
 
@@ -513,9 +516,9 @@ void orc_aspt_spmm(const orc_aspt *t, const float *B, int k, float *C) {
   }
 }
 
-int orc_num_threads(void) {
+int orc_num_threads(void) { /* host cores available to the process, whatever OMP_NUM_THREADS says */
 #ifdef _OPENMP
-  return omp_get_max_threads();
+  return omp_get_num_procs();
 #else
   return 1;
 #endif
