@@ -115,7 +115,7 @@ ABI_SYMBOLS = [
     "fx_csr_from_arrays", "fx_csr_from_device", "fx_mtx_load", "fx_csr_write_csv", "fx_csr_save_bin", "fx_csr_load_bin", "fx_matrix_get_info", "fx_matrix_host_csr",
     "fx_matrix_device_csr", "fx_matrix_free", "fx_rand_B", "fx_reorder", "fx_reorder_with_rank",
     "fx_permutation", "fx_permute_rows", "fx_unpermute_rows", "fx_build", "fx_rebuild",
-    "fx_tiles_export_aspt", "fx_tiles_export_tile", "fx_tiles_export_seg", "fx_tiles_export_pillar", "fx_tiles_export_tcw", "fx_tiles_tcw_info", "fx_tiles_free", "fx_spmm", "fx_spmm_kernel_times", "fx_spmm_host", "fx_check",
+    "fx_tiles_export_aspt", "fx_tiles_export_tile", "fx_tiles_export_seg", "fx_tiles_export_pillar", "fx_tiles_export_tcw", "fx_tiles_tcw_info", "fx_tiles_free", "fx_spmm", "fx_spmm_kernel_times", "fx_spmm_host", "fx_comm_unique_id", "fx_comm_init", "fx_comm_free", "fx_comm_slice", "fx_spmm_sharded_host", "fx_check",
 ]
 
 
@@ -163,6 +163,12 @@ def lib():
     L.fx_spmm.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(C.c_float)]
     L.fx_spmm_kernel_times.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(C.c_float)]
     L.fx_spmm_host.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.fx_comm_unique_id.argtypes = [C.c_char_p]
+    L.fx_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p, C.POINTER(vp)]
+    L.fx_comm_free.argtypes = [vp]
+    L.fx_comm_free.restype = None
+    L.fx_comm_slice.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.fx_spmm_sharded_host.argtypes = [vp, vp, vp, vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.fx_check.argtypes = [vp, vp, C.c_int64, C.c_int, vp, C.POINTER(Report)]
     _lib = L
     return L
@@ -459,6 +465,40 @@ class Mat:
             self.free()
         except Exception:
             pass
+
+
+class Comm:
+    """fx_comm: the NCCL communicator of the sharded host path (include/flexb200.h, L3b).  `broadcast_bytes(bytes_or_None)`
+    is the host program's way of sending rank 0's 128-byte unique id to every rank (torch.distributed, MPI, ...)."""
+
+    def __init__(self, nranks, rank, broadcast_bytes):
+        uid = C.create_string_buffer(128)
+        if rank == 0:
+            _ck(lib().fx_comm_unique_id(uid))
+        raw = broadcast_bytes(uid.raw if rank == 0 else None)
+        assert len(raw) == 128
+        self._h = C.c_void_p()
+        self.nranks, self.rank = nranks, rank
+        _ck(lib().fx_comm_init(nranks, rank, C.create_string_buffer(raw, 128), C.byref(self._h)))
+
+    def slice(self, n):
+        lo, hi = C.c_int64(), C.c_int64()
+        _ck(lib().fx_comm_slice(self._h, int(n), C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def spmm_sharded_host(self, mat, B_rows, C_local):
+        """B_rows: this rank's rows of B, C_local: this rank's rows of C (C-contiguous float32 numpy arrays, ideally pinned).
+        Returns (total_ms, tElap_ms) on this rank's device clock."""
+        k = C_local.shape[1]
+        tot, tk = C.c_float(), C.c_float()
+        _ck(lib().fx_spmm_sharded_host(mat._h, self._h, B_rows.ctypes.data if B_rows.size else None, C_local.ctypes.data, k,
+                                       C.byref(tot), C.byref(tk)))
+        return tot.value, tk.value
+
+    def free(self):
+        if self._h:
+            lib().fx_comm_free(self._h)
+            self._h = C.c_void_p()
 
 
 def check(gold, res, rowptr=None):

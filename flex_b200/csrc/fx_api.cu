@@ -87,6 +87,10 @@ extern "C" int fx_build(const fx_matrix* m, const fx_build_opts* opts, fx_tiles*
       if (t->opts.tc_min_gain) w.min_gain = std::max(0, t->opts.tc_min_gain);  // negative = no minimum
       if (t->opts.tc_chunk_cost) w.chunk_cost = std::max(0, t->opts.tc_chunk_cost);
       if (t->opts.tc_min_total) w.min_total = std::max(0, t->opts.tc_min_total);
+      // The whole-matrix gate is a statement about the MATRIX (do its windows pay for a second kernel?): a row-panel shard
+      // answers for its share of the nz, so that 1/8 shards of a matrix that keeps its windows keep theirs (with an absolute
+      // threshold every shard of Reddit-shape at 8 GPUs fell back to the slower ASpT path).
+      if (m->nnz > 0 && t->nnz_local < m->nnz) w.min_total = w.min_total * t->nnz_local / m->nnz;
       if (w.T < 2 || w.W < 32 || w.W > 4096 || w.W % 32) { fx::set_error("tc_threshold must be >= 2 and tc_width a multiple of 32 in [32,4096]"); return fail(FX_ERR_ARG); }
       extra = fx::tcw_arena_bytes(t);
     }

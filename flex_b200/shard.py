@@ -41,7 +41,12 @@ def gather_rows(dist, local_rows, shards, k, device=None):
 
 
 class ShardedHostSpmm:
-    """C = A*B from HOST buffers on G ranks without sending B over PCIe G times.
+    """CPU-testable restatement (torch.distributed, any backend) of the exchange that the PRODUCT path performs in C:
+    `fx_spmm_sharded_host` (include/flexb200.h L3b, flex_b200/csrc/fx_shard.cu; `flex_b200.Comm` binds it) -- same slicing
+    rule, same all-gather, same shard multiply.  tests/test_shard_gloo.py drives this class with gloo and the oracle; the
+    GPU path is checked in bench.py against fx_spmm_host on every rank.
+
+    C = A*B from HOST buffers on G ranks without sending B over PCIe G times.
 
     `fx_spmm_host` on every rank copies all of B to its GPU (B is replicated), so at G ranks the host
     feeds G * n*k*4 bytes through its PCIe root per SpMM and the end-to-end time grows with G (8 GPUs,

@@ -231,6 +231,28 @@ int fx_spmm_kernel_times(const fx_tiles *t, const float *B_dev, float *C_dev, in
 int fx_spmm_host(const fx_tiles *t, const float *B_host, float *C_host, int k, float *total_ms,
                  float *tElap_ms);
 
+/* ---- L3b: row-panel sharded SpMM from host buffers (the reference is single-GPU: no counterpart) ------
+ * One process per GPU.  Every rank builds the tiles of ITS row-panel shard (fx_build with row_begin/row_end; B is
+ * replicated, no collective is on the multiply itself).  What a G-rank job must not do is push all of B through the
+ * host's PCIe root G times: rank r uploads rows [r*ceil(n/G), (r+1)*ceil(n/G)) of B only, ncclAllGather assembles B on
+ * every GPU over NVLink -- the one real exchange step of the path --, the rank multiplies its shard and copies its own
+ * rows of C back, pipelined over column chunks like fx_spmm_host.
+ * fx_comm wraps an ncclComm_t created from a unique id that the host program distributes (MPI, torch.distributed,
+ * a file ...): rank 0 calls fx_comm_unique_id and hands the 128 bytes to every rank, every rank calls fx_comm_init
+ * on its device.  NCCL is resolved at run time (the libnccl.so.2 already loaded in the process, else the system's);
+ * without it these calls return FX_ERR_UNSUPPORTED and everything else works. */
+typedef struct fx_comm fx_comm;
+int fx_comm_unique_id(char id[128]);
+int fx_comm_init(int nranks, int rank, const char id[128], fx_comm **out);
+void fx_comm_free(fx_comm *c);
+/* rows [*row_lo, *row_hi) of B that this rank uploads for a matrix of n rows */
+int fx_comm_slice(const fx_comm *c, int64_t n, int64_t *row_lo, int64_t *row_hi);
+/* B_rows_host: this rank's rows of B (row stride k); C_local_host: rows [row_begin,row_end) of C (row stride k).
+ * Collective: every rank of the communicator must call it with the same k.  total_ms = first H2D to last D2H on this
+ * rank's device clock; tElap_ms = kernels only.  ASpT / tensor-window tiles, k % 4 == 0, k <= the build's k. */
+int fx_spmm_sharded_host(const fx_tiles *t, fx_comm *c, const float *B_rows_host, float *C_local_host, int k,
+                         float *total_ms, float *tElap_ms);
+
 /* ---- L4: validation + reporting ----------------------------------------------------- */
 /* resCheck (flex.cu:4155-4213) and the ASpT validator (aspt/sspmm_128.cu:1425-1446) over host
  * buffers; rowptr may be NULL (row_nnz taken as 1). */

@@ -65,6 +65,10 @@ def plan(rowptr, col, val, T=4, W=256, min_gain=1024, chunk_cost=224, min_total=
     val = np.asarray(val, np.float32)[base:rowptr[row_end]]
     sel = [select_columns(col[rp[p * BH]:rp[min(n, p * BH + BH)]], T, W, min_gain, chunk_cost) for p in range(npanel)]
     net_gain = sum(g for _, g in sel)
+    # a row-panel shard answers the whole-matrix gate for its share of the nz (integer floor, as fx_build does)
+    nnz_all, nnz_loc = int(rowptr[-1]), int(rowptr[row_end] - base)
+    if 0 < nnz_loc < nnz_all:
+        min_total = min_total * nnz_loc // nnz_all
     if net_gain < min_total:  # the windows together do not pay for a second kernel
         sel = [(np.zeros(0, np.int64), 0)] * npanel
     assert W % 32 == 0
