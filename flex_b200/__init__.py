@@ -115,7 +115,7 @@ ABI_SYMBOLS = [
     "fx_csr_from_arrays", "fx_csr_from_device", "fx_mtx_load", "fx_csr_write_csv", "fx_csr_save_bin", "fx_csr_load_bin", "fx_matrix_get_info", "fx_matrix_host_csr",
     "fx_matrix_device_csr", "fx_matrix_free", "fx_rand_B", "fx_reorder", "fx_reorder_with_rank",
     "fx_permutation", "fx_permute_rows", "fx_unpermute_rows", "fx_build", "fx_rebuild",
-    "fx_tiles_export_aspt", "fx_tiles_export_tile", "fx_tiles_export_seg", "fx_tiles_export_pillar", "fx_tiles_export_tcw", "fx_tiles_tcw_info", "fx_tiles_free", "fx_spmm", "fx_spmm_kernel_times", "fx_spmm_host", "fx_comm_unique_id", "fx_comm_init", "fx_comm_free", "fx_comm_slice", "fx_spmm_sharded_host", "fx_check",
+    "fx_tiles_export_aspt", "fx_tiles_export_tile", "fx_tiles_export_seg", "fx_tiles_export_pillar", "fx_tiles_export_tcw", "fx_tiles_tcw_info", "fx_tiles_free", "fx_spmm", "fx_spmm_kernel_times", "fx_spmm_host", "fx_set_device", "fx_panel_shards", "fx_comm_unique_id", "fx_comm_init", "fx_comm_free", "fx_comm_slice", "fx_spmm_sharded_host", "fx_check",
 ]
 
 
@@ -163,6 +163,8 @@ def lib():
     L.fx_spmm.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(C.c_float)]
     L.fx_spmm_kernel_times.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(C.c_float)]
     L.fx_spmm_host.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.fx_set_device.argtypes = [C.c_int]
+    L.fx_panel_shards.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]
     L.fx_comm_unique_id.argtypes = [C.c_char_p]
     L.fx_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p, C.POINTER(vp)]
     L.fx_comm_free.argtypes = [vp]
@@ -254,6 +256,12 @@ class DataLoader:
     dim = property(lambda s: s.info.dim)
     graph_name = property(lambda s: s.info.graph_name.decode())
     vertex_order_abbr = property(lambda s: s.info.order_abbr.decode())
+
+    def panel_shards(self, nranks):
+        """[(lo, hi)] per rank: the library's row-panel sharding rule (fx_panel_shards)."""
+        cuts = (C.c_int64 * (nranks + 1))()
+        _ck(lib().fx_panel_shards(self._h, int(nranks), cuts))
+        return [(int(cuts[r]), int(cuts[r + 1])) for r in range(nranks)]
 
     def host_csr(self):
         rp, c, v = C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -206,6 +206,32 @@ extern "C" int fx_spmm(const fx_tiles* t, const float* B_dev, float* C_dev, int 
   return FX_OK;
 }
 
+extern "C" int fx_set_device(int ordinal) {
+  if (int rc = check_device()) return rc;
+  FX_CUDA(cudaSetDevice(ordinal));
+  return FX_OK;
+}
+
+// Row-panel shards of the multi-GPU path: contiguous ranges of 128-row panels with about nnz/G nonzeros each, cut by
+// prefix sums over rowPtr (the rule flex_b200/shard.py:panel_shards states for the CPU tests).
+extern "C" int fx_panel_shards(const fx_matrix* m, int nranks, int64_t* cuts) {
+  FX_REQUIRE(m && cuts && nranks >= 1, FX_ERR_ARG, "fx_panel_shards: bad argument");
+  const int64_t n = m->n, npanel = (n + 127) / 128, total = m->rowptr.empty() ? 0 : (int64_t)m->rowptr[n];
+  auto pnnz = [&](int64_t p) { return (int64_t)m->rowptr[std::min<int64_t>(p * 128, n)]; };
+  int64_t prev = 0;
+  cuts[0] = 0;
+  for (int r = 1; r < nranks; ++r) {
+    // first panel boundary whose nz prefix reaches total*r/nranks (numpy searchsorted, side="left", on the prefix)
+    const double want = (double)total * r / nranks;
+    int64_t lo = 0, hi = npanel + 1;
+    while (lo < hi) { const int64_t mid = (lo + hi) / 2; if ((double)pnnz(mid) < want) lo = mid + 1; else hi = mid; }
+    prev = std::max(prev, std::min(lo, npanel));
+    cuts[r] = std::min<int64_t>(prev * 128, n);
+  }
+  cuts[nranks] = n;
+  return FX_OK;
+}
+
 extern "C" int fx_spmm_kernel_times(const fx_tiles* t, const float* B_dev, float* C_dev, int k, void* stream, float ms[4]) {
   FX_REQUIRE(t && B_dev && C_dev && k > 0 && ms, FX_ERR_ARG, "fx_spmm_kernel_times: bad argument");
   FX_REQUIRE((t->format == FX_FMT_ASPT || t->format == FX_FMT_TCW) && k % 4 == 0 && k <= t->k, FX_ERR_UNSUPPORTED,

@@ -242,6 +242,11 @@ int fx_spmm_host(const fx_tiles *t, const float *B_host, float *C_host, int k, f
  * on its device.  NCCL is resolved at run time (the libnccl.so.2 already loaded in the process, else the system's);
  * without it these calls return FX_ERR_UNSUPPORTED and everything else works. */
 typedef struct fx_comm fx_comm;
+/* cudaSetDevice for host programs that do not include the CUDA headers (one process per GPU: call it first) */
+int fx_set_device(int ordinal);
+/* the row-panel shards of a G-rank job: rank r owns rows [cuts[r], cuts[r+1]) -- contiguous ranges of 128-row panels
+ * holding about nnz/G nonzeros each (cuts has nranks+1 entries) */
+int fx_panel_shards(const fx_matrix *m, int nranks, int64_t *cuts);
 int fx_comm_unique_id(char id[128]);
 int fx_comm_init(int nranks, int rank, const char id[128], fx_comm **out);
 void fx_comm_free(fx_comm *c);
