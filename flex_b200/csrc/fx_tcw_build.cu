@@ -39,7 +39,12 @@ namespace {
 
 constexpr int BH = 128;
 constexpr int CAND_CAP = 8192;
-constexpr unsigned CNT_MASK = 0xFFFFFFu;
+// A column counter of k_tcw_select: bits 0-7 the count (at most 128: columns are unique within a row), bits 8-13 the
+// "registered in doubling round r" flags, bits 14-30 the EPOCH of the panel that last touched it (a counter of an older
+// epoch reads as zero, so the kernel never walks the panel a third time to zero what it touched), bit 31 = MARK | slot.
+constexpr unsigned CNT_MASK = 0xFFu;
+constexpr int FLAG_SHIFT = 8, EPOCH_SHIFT = 14;
+constexpr unsigned EPOCH_MAX = (1u << (31 - EPOCH_SHIFT)) - 1;
 constexpr unsigned MARK = 0x80000000u;
 constexpr int MAX_CH = 128;  // W <= 4096
 
@@ -85,21 +90,45 @@ __global__ void __launch_bounds__(512) k_tcw_select(const int* __restrict__ csr_
   __shared__ int hist[MAX_CH];
   __shared__ int s_ns;
   __shared__ long long s_gain;
+  __shared__ int s_rp[BH + 1], s_wl[BH];
   const int CH = W / 32;
   unsigned* cnt = cnt_all + (size_t)blockIdx.x * ncols;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int p = blockIdx.x; p < npanel; p += gridDim.x) {
+  __shared__ int s_panel;
+  unsigned epoch = 0;
+  // Panels are handed out by a counter (stats[6]): a panel that holds hub rows takes several times the average, and a fixed
+  // stride left the kernel waiting for the CTA that drew the most of them.  Every panel's output depends on the panel alone.
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_panel = (int)atomicAdd(&stats[6], 1ull);
+    __syncthreads();
+    const int p = s_panel;
+    if (p >= npanel) break;
     const int lb = csr_v[p * BH], ub = csr_v[(p + 1) * BH];
     if (threadIdx.x == 0) s_nc = 0;
+    if (++epoch > EPOCH_MAX) {  // the epoch field is full: zero this CTA's counters and start over
+      for (int i = threadIdx.x; i < ncols; i += blockDim.x) cnt[i] = 0u;
+      epoch = 1;
+    }
+    const unsigned ebase = epoch << EPOCH_SHIFT;
     __syncthreads();
-    // pass 1: count; the T-th hit of a column registers it
-    for (int e = lb + threadIdx.x; e < ub; e += blockDim.x) {
-      const unsigned c = col[e];
-      const unsigned old = atomicAdd(&cnt[c], 1u);
-      if ((int)old == T - 1) {
-        const int pos = atomicAdd(&s_nc, 1);
-        if (pos < CAND_CAP) skeys[pos] = c;
-      }
+    // pass 1: count; the T-th hit of a column registers it.  Four independent (column load, atomic) pairs per thread and
+    // step: the kernel waits on exactly these round trips (long scoreboard 54 % of its stall samples)
+    for (int e0 = lb + threadIdx.x; e0 < ub; e0 += 4 * blockDim.x) {
+      unsigned c[4], old[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[j] = e0 + j * (int)blockDim.x < ub ? col[e0 + j * (int)blockDim.x] : 0xFFFFFFFFu;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c[j] != 0xFFFFFFFFu) atomicMax(&cnt[c[j]], ebase);  // a counter of an older epoch starts over (no return value needed)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) old[j] = c[j] != 0xFFFFFFFFu ? (atomicAdd(&cnt[c[j]], 1u) & CNT_MASK) : 0xFFFFFFFFu;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((int)old[j] == T - 1 && c[j] != 0xFFFFFFFFu) {
+          const int pos = atomicAdd(&s_nc, 1);
+          if (pos < CAND_CAP) skeys[pos] = c[j];
+        }
     }
     __syncthreads();
     int nc = s_nc;
@@ -109,7 +138,7 @@ __global__ void __launch_bounds__(512) k_tcw_select(const int* __restrict__ csr_
       __syncthreads();
       if (threadIdx.x == 0) s_nc = 0;
       __syncthreads();
-      const unsigned bit = 1u << (24 + round);
+      const unsigned bit = 1u << (FLAG_SHIFT + round);
       for (int e = lb + threadIdx.x; e < ub; e += blockDim.x) {
         const unsigned c = col[e];
         if ((int)(cnt[c] & CNT_MASK) >= Tcur) {
@@ -165,23 +194,34 @@ __global__ void __launch_bounds__(512) k_tcw_select(const int* __restrict__ csr_
     if (threadIdx.x == 0) tc_ncol[p] = ns;
     for (int i = threadIdx.x; i < CH; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    // pass 2: window nz of every row and of every 32-column chunk of the list
-    for (int r = warp; r < BH; r += nwarp) {
-      int n = 0;
-      if (ns > 0) {
-        const int lo = csr_v[p * BH + r], hi = csr_v[p * BH + r + 1];
-        for (int e = lo + lane; e < hi; e += 32) {
-          const unsigned f = cnt[col[e]];
-          if (f >> 31) { ++n; atomicAdd(&hist[(f & 0xFFFFu) >> 5], 1); }
-        }
-        n = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), n, cg::plus<int>());
+    // pass 2: window nz of every row and of every 32-column chunk of the list.  All threads stride over the panel's nz
+    // (a warp per row left the CTA waiting for the warp that drew a hub row: barrier 30 % of the stall samples); the row
+    // of a nz is found in the panel's 129 row pointers in shared memory.
+    for (int i = threadIdx.x; i <= BH; i += blockDim.x) { s_rp[i] = csr_v[p * BH + i]; if (i < BH) s_wl[i] = 0; }
+    __syncthreads();
+    if (ns > 0) {
+      for (int e0 = lb + threadIdx.x; e0 < ub; e0 += 4 * blockDim.x) {
+        unsigned f[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[j] = e0 + j * (int)blockDim.x < ub ? cnt[col[e0 + j * (int)blockDim.x]] : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (f[j] >> 31) {
+            const int e = e0 + j * (int)blockDim.x;
+            int lo = 0, hi = BH;  // last row whose first nz is <= e
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_rp[mid] <= e) lo = mid; else hi = mid; }
+            atomicAdd(&s_wl[lo], 1);
+            atomicAdd(&hist[(f[j] & 0xFFFFu) >> 5], 1);
+          }
       }
-      if (lane == 0) win_len[p * BH + r] = n;
     }
     __syncthreads();
+    for (int i = threadIdx.x; i < BH; i += blockDim.x) win_len[p * BH + i] = s_wl[i];
+    __syncthreads();
     for (int i = threadIdx.x; i < CH; i += blockDim.x) chunk_len[(size_t)p * CH + i] = hist[i];
-    // pass 3: leave the counters zeroed
-    for (int e = lb + threadIdx.x; e < ub; e += blockDim.x) cnt[col[e]] = 0u;
+    // only the marks have to go (they outrank every epoch); counts of this panel are stale for the next one by their epoch,
+    // and the whole scratch is cleared once at the end of the build
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) cnt[(unsigned)skeys[i]] = 0u;
     __syncthreads();
   }
 }
@@ -254,26 +294,42 @@ __global__ void __launch_bounds__(512) k_tcw_split(const int* __restrict__ csr_v
                                                    const int* __restrict__ tc_ncol, int npanel, int ncols, int W,
                                                    unsigned* __restrict__ cnt_all, uint16_t* __restrict__ win_code,
                                                    float* __restrict__ win_val, uint32_t* __restrict__ rest_col,
-                                                   float* __restrict__ rest_val) {
+                                                   float* __restrict__ rest_val, unsigned long long* __restrict__ sched) {
   extern __shared__ int off2[];  // [CH][128] nz of (chunk, row), then their exclusive scan
   __shared__ int wsum[16];
+  __shared__ int s_rp[BH + 1];
   unsigned* cnt = cnt_all + (size_t)blockIdx.x * ncols;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const int CH = W / 32, n2 = CH * BH;
-  for (int p = blockIdx.x; p < npanel; p += gridDim.x) {
+  __shared__ int s_panel;
+  for (;;) {  // panels by a counter, as in k_tcw_select
+    __syncthreads();
+    if (threadIdx.x == 0) s_panel = (int)atomicAdd(sched, 1ull);
+    __syncthreads();
+    const int p = s_panel;
+    if (p >= npanel) break;
     const int ns = tc_ncol[p];
     const int* list = tc_cols + (size_t)p * W;
     for (int i = threadIdx.x; i < ns; i += blockDim.x) cnt[list[i]] = MARK | (unsigned)i;
     if (ns > 0) for (int i = threadIdx.x; i < n2; i += blockDim.x) off2[i] = 0;
+    for (int i = threadIdx.x; i <= BH; i += blockDim.x) s_rp[i] = csr_v[p * BH + i];
     __syncthreads();
     if (ns > 0) {
-      for (int r = warp; r < BH; r += nwarp) {
-        const int lo = csr_v[p * BH + r], hi = csr_v[p * BH + r + 1];
-        for (int e = lo + lane; e < hi; e += 32) {
-          const unsigned f = cnt[col[e]];
-          if (f >> 31) atomicAdd(&off2[((f & 0xFFFFu) >> 5) * BH + r], 1);
-        }
+      // nz of every (chunk, row): all threads stride over the panel's nz, the row of a nz comes from the panel's row pointers
+      const int lb = s_rp[0], ub = s_rp[BH];
+      for (int e0 = lb + threadIdx.x; e0 < ub; e0 += 4 * blockDim.x) {
+        unsigned f[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[j] = e0 + j * (int)blockDim.x < ub ? cnt[col[e0 + j * (int)blockDim.x]] : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (f[j] >> 31) {
+            const int e = e0 + j * (int)blockDim.x;
+            int lo = 0, hi = BH;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_rp[mid] <= e) lo = mid; else hi = mid; }
+            atomicAdd(&off2[((f[j] & 0xFFFFu) >> 5) * BH + lo], 1);
+          }
       }
       __syncthreads();
       // exclusive scan of off2 in (chunk, row) order
@@ -301,12 +357,16 @@ __global__ void __launch_bounds__(512) k_tcw_split(const int* __restrict__ csr_v
       const int lo = csr_v[row], hi = csr_v[row + 1];
       int ro = lo - win_rowptr[row];
       int last_ch = -1, last_cnt = 0;
+      // the (column, value, counter) loads of the next step are requested before this step's ranks are worked out
+      unsigned c_n = 0, f_n = 0;
+      float v_n = 0.f;
+      if (lo + lane < hi) { c_n = col[lo + lane]; v_n = val[lo + lane]; f_n = ns > 0 ? cnt[c_n] : 0u; }
       for (int e0 = lo; e0 < hi; e0 += 32) {
         const int e = e0 + lane;
         const bool valid = e < hi;
-        unsigned c = 0, f = 0;
-        float v = 0.f;
-        if (valid) { c = col[e]; v = val[e]; f = ns > 0 ? cnt[c] : 0u; }
+        const unsigned c = c_n, f = valid ? f_n : 0u;
+        const float v = v_n;
+        if (e + 32 < hi) { c_n = col[e + 32]; v_n = val[e + 32]; f_n = ns > 0 ? cnt[c_n] : 0u; }
         const bool isw = (f >> 31) != 0u;
         const unsigned mw = __ballot_sync(0xffffffffu, isw), mr = __ballot_sync(0xffffffffu, valid && !isw);
         int ch = -1, pc = 0;
@@ -421,8 +481,11 @@ int tcw_build(fx_tiles* t, cudaStream_t s) {
   static SmemAttr split_attr;
   if (int rc = split_attr.ensure(k_tcw_split, split_smem)) return rc;
   k_tcw_split<<<a.G, 512, split_smem, s>>>(w.csr_v, col, val, w.win_rowptr, w.win_cptr, w.tc_cols, w.tc_ncol, a.npanel, (int)m->n,
-                                           w.W, a.cnt_scratch, w.win_code, w.win_val, w.rest_col, w.rest_val);
+                                           w.W, a.cnt_scratch, w.win_code, w.win_val, w.rest_col, w.rest_val, w.stats + 7);
   FX_LAUNCH_CHECK();
+  // k_tcw_select leaves stale (epoch, count) words behind; the ASpT builder expects zeros (a streaming memset: 46 us for the
+  // 276 MB of Reddit-shape, against the ~0.3 ms the third pass over every panel's nz cost)
+  FX_CUDA(cudaMemsetAsync(a.cnt_scratch, 0, sizeof(unsigned) * (size_t)a.G * (size_t)m->n, s));
   FX_CUDA(cudaMemcpyAsync(t->stats_host, w.stats, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
   FX_CUDA(cudaStreamSynchronize(s));
   w.win_nnz = (long long)t->stats_host[0];

@@ -31,5 +31,13 @@ if [ -x "$NVCC" ] && [ "${REF_ASPT:-1}" = "1" ]; then
     fi
   done
   wait
+  # the same sources behind a wrapper that dumps the reference's tile format after it ran (pins A1: ref_aspt_dump.cu)
+  for b in sspmm_128 sspmm_32; do
+    if [ ! -f "$OUT/${b}_dump" ] || [ "$HERE/ref_aspt_dump.cu" -nt "$OUT/${b}_dump" ]; then
+      (cd "$REF/aspt" && $NVCC -std=c++17 -O3 -w -gencode arch=compute_100,code=sm_100 -ccbin /usr/bin/g++ -I"$REF/aspt" \
+         -DREF_SRC="\"$REF/aspt/$b.cu\"" "$HERE/ref_aspt_dump.cu" -o "$OUT/${b}_dump") &
+    fi
+  done
+  wait
 fi
 echo "oracle/_ref built: $(ls "$OUT" | tr '\n' ' ')"
