@@ -15,6 +15,8 @@
 #include <cooperative_groups/reduce.h>
 #include <cooperative_groups/scan.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "fx_common.cuh"
 #include "fx_scan.cuh"
 
@@ -426,6 +428,30 @@ __global__ void k_fill_special(const int* __restrict__ spec_cnt, const int* __re
   for (int j = 0; j < c; ++j) { special[o + j] = i; special2[o + j] = STHRESHOLD * j; }
 }
 
+// L2-residency scheduling of the 512-chunks (the idea of the reference's segment re-ordering, mat.cu:366
+// dfsSegs / :527 sliWinSegs: run next to each other what reads the same rows of B).  A chunk is 512 consecutive nz of one
+// long row, i.e. a contiguous range of COLUMNS; in row order, neighbouring CTAs of k_spmm_special_cta read unrelated ranges
+// and every row of B comes from DRAM several times per SpMM.  The chunks are executed in the order of the first column they
+// read instead (key below, radix-sorted), so the CTAs in flight at any time share one slice of B in L2.  partial[] stays
+// indexed by chunk id: only the execution order changes, the result is bit-identical.
+__global__ void k_special_keys(const int* __restrict__ special, const int* __restrict__ special2, const int* __restrict__ spec_off,
+                               const int* __restrict__ mcsr_cnt, const int* __restrict__ mcsr_e, const int* __restrict__ csr_e,
+                               int nr, int cap, unsigned* __restrict__ keys, int* __restrict__ iota) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  iota[i] = i;
+  unsigned key = 0xFFFFFFFFu;
+  if (i < spec_off[nr]) {
+    const int row = special[i], off = special2[i];
+    const int p = row / BH, r = row % BH;
+    const int cnt0 = mcsr_cnt[p], delta = mcsr_cnt[p + 1] - cnt0;
+    const int nch = spec_off[row + 1] - spec_off[row];
+    const int lo = mcsr_e[cnt0 * BH + (r + 1) * delta] - nch * STHRESHOLD + off;
+    key = (unsigned)csr_e[lo];
+  }
+  keys[i] = key;
+}
+
 }  // namespace
 
 namespace fx {
@@ -471,6 +497,10 @@ int aspt_carve(fx_tiles* t, int64_t ncols, size_t extra_bytes) {
   add(sizeof(float) * (ne + 2));                     // csr_ev
   add(sizeof(int) * (nr + 2) * 2);                   // spec_cnt, spec_off
   add(sizeof(int) * (size_t)a.special_cap * 2);
+  add(sizeof(int) * (size_t)a.special_cap * 4);  // spec_order, spec_iota, spec_keys, spec_keys_out
+  cub::DeviceRadixSort::SortPairs(nullptr, a.spec_sort_tmp_bytes, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr,
+                                  (int*)nullptr, a.special_cap);
+  add(a.spec_sort_tmp_bytes);
   add(sizeof(unsigned long long) * 16);
   add(sizeof(float) * a.partial_cap_floats);
   a.wl_cap = (int)(npanel * 2 + ne / 4096 + 32);
@@ -499,6 +529,11 @@ int aspt_carve(fx_tiles* t, int64_t ncols, size_t extra_bytes) {
   a.spec_off = A.take<int>(nr + 2);
   a.special = A.take<int>(a.special_cap);
   a.special2 = A.take<int>(a.special_cap);
+  a.spec_order = A.take<int>(a.special_cap);
+  a.spec_iota = A.take<int>(a.special_cap);
+  a.spec_keys = A.take<unsigned>(a.special_cap);
+  a.spec_keys_out = A.take<unsigned>(a.special_cap);
+  a.spec_sort_tmp = A.take<char>(a.spec_sort_tmp_bytes);
   a.stats = A.take<unsigned long long>(16);
   a.wl_all = A.take<int2>(a.wl_cap);
   a.wl_plain = A.take<int2>(a.wl_cap);
@@ -563,6 +598,14 @@ int aspt_build(fx_tiles* t, cudaStream_t s) {
   FX_LAUNCH_CHECK();
   k_fill_special<<<ceil_div(a.nr, 256), 256, 0, s>>>(a.spec_cnt, a.spec_off, a.nr, a.special, a.special2);
   FX_LAUNCH_CHECK();
+  {  // execution order of the chunks: by the first column they read
+    k_special_keys<<<ceil_div(a.special_cap, 256), 256, 0, s>>>(a.special, a.special2, a.spec_off, a.mcsr_cnt, a.mcsr_e_use, a.csr_e_use,
+                                                              a.nr, a.special_cap, a.spec_keys, a.spec_iota);
+    FX_LAUNCH_CHECK();
+    size_t tmp = a.spec_sort_tmp_bytes;
+    FX_CUDA(cub::DeviceRadixSort::SortPairs(a.spec_sort_tmp, tmp, a.spec_keys, a.spec_keys_out, a.spec_iota, a.spec_order, a.special_cap,
+                                            0, 32, s));  // padding keys (0xFFFFFFFF) sort to the end
+  }
   // Heaviest entries first only when the grid is a few waves long (at most 6 panels per SM; the row kernel runs 3 CTAs per SM): there the
   // tail is what counts (flickr-shape, 698 panels: 0.087 -> 0.073 ms); on long grids the panel order is worth more, because
   // neighbouring panels share B rows in L2 (yelp-shape 0.576 -> 0.593 ms, Amazon-shape 6.55 -> 7.34 ms; Reddit-shape equal).

@@ -139,6 +139,11 @@ struct fx_aspt_dev {  // device-side ASpT format (aspt/sspmm_128.cu:76-90 global
   unsigned* cnt_scratch = nullptr;  // G x ncols saturating per-column counters (kept zeroed)
   int G = 0;
   int *spec_cnt = nullptr, *spec_off = nullptr, *special = nullptr, *special2 = nullptr;
+  // execution order of the 512-chunks (L2-residency scheduling): chunk ids sorted by the first column they read
+  int *spec_order = nullptr, *spec_iota = nullptr;
+  unsigned *spec_keys = nullptr, *spec_keys_out = nullptr;
+  void* spec_sort_tmp = nullptr;
+  size_t spec_sort_tmp_bytes = 0;
   int *plist_plain = nullptr, *plist_tiled = nullptr;  // panels without / with dense tiles (ascending)
   int n_plain = 0, n_tiled = 0;
   // work lists of the SpMM launches: one entry per CTA = (panel, part | parts << 8); a panel with several times

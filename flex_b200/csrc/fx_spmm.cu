@@ -159,6 +159,7 @@ struct PanelArgs {
   const int* csr_e;
   const float* csr_ev;
   const int* spec_off;   // nullptr: rows are never split
+  const int* spec_order; // execution order of the 512-chunks (chunk ids sorted by first column), nullptr = list order
   const float* partial;  // [chunk][k] partial sums of the 512-chunks
   const float* B;
   float* C;
@@ -214,7 +215,8 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special_cta(PanelArgs
   auto tile = cg::tiled_partition<LPR>(cg::this_thread_block());
   const int sl = tile.thread_rank();
   const int wk = (threadIdx.x >> 5) * RPW + (threadIdx.x & 31) / LPR;
-  const int item = blockIdx.x, kc0 = blockIdx.y * KC;
+  // chunks run in the order of the columns they read (fx_aspt_build.cu:k_special_keys); partial[] is indexed by chunk id
+  const int item = a.spec_order ? a.spec_order[blockIdx.x] : (int)blockIdx.x, kc0 = blockIdx.y * KC;
   const unsigned k4 = a.k / 4;
   const bool col_ok = kc0 / 4 + sl < a.width / 4;
   const int c4 = col_ok ? kc0 / 4 + sl : 0;
@@ -723,6 +725,8 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   FX_REQUIRE((size_t)special_p * (size_t)k <= d.partial_cap_floats, FX_ERR_ARG,
              "fx_spmm: k = %d is larger than the k = %d the tiles were built for", k, t->k);
   a.spec_off = special_p > 0 ? d.spec_off : nullptr;
+  static const bool spec_sched = !(getenv("FLEX_SPEC_ORDER") && atoi(getenv("FLEX_SPEC_ORDER")) == 0);
+  a.spec_order = spec_sched ? d.spec_order : nullptr;
   a.partial = d.partial;
   a.B = B; a.C = C;
   a.npanel = d.npanel; a.nloc = t->row_end - t->row_begin; a.k = k; a.width = width; a.BW = d.BW;
