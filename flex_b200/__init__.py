@@ -115,7 +115,7 @@ ABI_SYMBOLS = [
     "fx_csr_from_arrays", "fx_csr_from_device", "fx_mtx_load", "fx_csr_write_csv", "fx_csr_save_bin", "fx_csr_load_bin", "fx_matrix_get_info", "fx_matrix_host_csr",
     "fx_matrix_device_csr", "fx_matrix_free", "fx_rand_B", "fx_reorder", "fx_reorder_with_rank",
     "fx_permutation", "fx_permute_rows", "fx_unpermute_rows", "fx_build", "fx_rebuild",
-    "fx_tiles_export_aspt", "fx_tiles_export_tile", "fx_tiles_export_seg", "fx_tiles_export_pillar", "fx_tiles_export_tcw", "fx_tiles_tcw_info", "fx_tiles_free", "fx_spmm", "fx_spmm_kernel_times", "fx_spmm_host", "fx_set_device", "fx_panel_shards", "fx_comm_unique_id", "fx_comm_init", "fx_comm_free", "fx_comm_slice", "fx_spmm_sharded_host", "fx_check",
+    "fx_tiles_export_aspt", "fx_tiles_export_tile", "fx_tiles_export_seg", "fx_tiles_export_pillar", "fx_tiles_export_tcw", "fx_tiles_tcw_info", "fx_tiles_free", "fx_spmm", "fx_spmm_kernel_times", "fx_axw", "fx_spmm_host", "fx_set_device", "fx_panel_shards", "fx_comm_unique_id", "fx_comm_init", "fx_comm_free", "fx_comm_slice", "fx_spmm_sharded_host", "fx_check",
 ]
 
 
@@ -162,6 +162,7 @@ def lib():
     L.fx_tiles_free.restype = None
     L.fx_spmm.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(C.c_float)]
     L.fx_spmm_kernel_times.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(C.c_float)]
+    L.fx_axw.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.fx_spmm_host.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.fx_set_device.argtypes = [C.c_int]
     L.fx_panel_shards.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]
@@ -450,6 +451,13 @@ class Mat:
         ms = (C.c_float * 4)()
         _ck(lib().fx_spmm_kernel_times(self._h, B_ptr, C_ptr, int(k), stream, ms))
         return {"k_spmm_tc": ms[0], "k_spmm_special_cta": ms[1], "k_spmm_rows": ms[2], "step": ms[3]}
+
+    def axw(self, X_ptr, W_ptr, C_ptr, k, c, order=0, stream=None, timed=False):
+        """C = A*(X*W) (order 0, cusp.cu run1) or (A*X)*W (order 1, run2) on device pointers; timed=True returns (gemm_ms, spmm_ms)."""
+        g, sp = C.c_float(), C.c_float()
+        _ck(lib().fx_axw(self._h, X_ptr, W_ptr, C_ptr, int(k), int(c), int(order), stream,
+                         C.byref(g) if timed else None, C.byref(sp) if timed else None))
+        return (g.value, sp.value) if timed else None
 
     def spmm_host(self, B, out=None):
         """Host buffers in, host buffer out (H2D + kernels + D2H)."""

@@ -131,7 +131,7 @@ extern "C" void fx_tiles_free(fx_tiles* t) {
   if (t->pipe_e0) cudaEventDestroy(t->pipe_e0);
   if (t->pipe_e1) cudaEventDestroy(t->pipe_e1);
   if (t->stats_host) cudaFreeHost(t->stats_host);
-  cudaFree(t->B_stage_dev); cudaFree(t->C_stage_dev);
+  cudaFree(t->B_stage_dev); cudaFree(t->C_stage_dev); cudaFree(t->axw_scratch);
   if (t->B_pinned) cudaFreeHost(t->B_pinned);
   if (t->C_pinned) cudaFreeHost(t->C_pinned);
   delete t;
@@ -237,6 +237,48 @@ extern "C" int fx_spmm_kernel_times(const fx_tiles* t, const float* B_dev, float
   FX_REQUIRE((t->format == FX_FMT_ASPT || t->format == FX_FMT_TCW) && k % 4 == 0 && k <= t->k, FX_ERR_UNSUPPORTED,
              "fx_spmm_kernel_times: ASpT / tensor-window handles, k %% 4 == 0 and k <= the build's k");
   return fx::spmm_aspt_times(t, B_dev, C_dev, k, static_cast<cudaStream_t>(stream), ms);
+}
+
+// AXW (cusp.cu:3-208, main.cu:22-79): order 0 = run1, C = A*(X*W); order 1 = run2, C = (A*X)*W
+extern "C" int fx_axw(const fx_tiles* tc, const float* X_dev, const float* W_dev, float* C_dev, int k, int c, int order,
+                      void* stream, float* gemm_ms, float* spmm_ms) {
+  FX_REQUIRE(tc && X_dev && W_dev && C_dev && k > 0 && c > 0 && (order == 0 || order == 1), FX_ERR_ARG, "fx_axw: bad argument");
+  FX_REQUIRE(k % 4 == 0 && c % 4 == 0, FX_ERR_UNSUPPORTED, "fx_axw: k and c must be multiples of 4");
+  fx_tiles* t = const_cast<fx_tiles*>(tc);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t n = t->mat->n, nloc = t->row_end - t->row_begin;
+  const size_t need = order == 0 ? (size_t)n * c : (size_t)std::max<int64_t>(nloc, 1) * k;
+  if (t->axw_cap < need) {
+    cudaFree(t->axw_scratch);
+    t->axw_scratch = nullptr; t->axw_cap = 0;
+    FX_CUDA(cudaMalloc(&t->axw_scratch, sizeof(float) * need));
+    t->axw_cap = need;
+  }
+  cudaEvent_t e[3] = {};
+  const bool timed = gemm_ms || spmm_ms;
+  if (timed) for (auto& x : e) FX_CUDA(cudaEventCreate(&x));
+  int rc = FX_OK;
+  if (timed) FX_CUDA(cudaEventRecord(e[0], s));
+  if (order == 0) {
+    rc = fx::gemm_xw(X_dev, W_dev, t->axw_scratch, n, k, c, s);            // B = X*W   (cusp.cu:30-32)
+    if (rc == FX_OK && timed) FX_CUDA(cudaEventRecord(e[1], s));
+    if (rc == FX_OK) rc = spmm_dispatch(t, t->axw_scratch, C_dev, c, s);     // C = A*B   (cusp.cu:62-83)
+  } else {
+    rc = spmm_dispatch(t, X_dev, t->axw_scratch, k, s);                      // B = A*X
+    if (rc == FX_OK && timed) FX_CUDA(cudaEventRecord(e[1], s));
+    if (rc == FX_OK) rc = fx::gemm_xw(t->axw_scratch, W_dev, C_dev, nloc, k, c, s);  // C = B*W
+  }
+  if (rc == FX_OK && timed) {
+    FX_CUDA(cudaEventRecord(e[2], s));
+    FX_CUDA(cudaEventSynchronize(e[2]));
+    float a = 0, b = 0;
+    FX_CUDA(cudaEventElapsedTime(&a, e[0], e[1]));
+    FX_CUDA(cudaEventElapsedTime(&b, e[1], e[2]));
+    if (gemm_ms) *gemm_ms = order == 0 ? a : b;
+    if (spmm_ms) *spmm_ms = order == 0 ? b : a;
+  }
+  if (timed) for (auto& x : e) cudaEventDestroy(x);
+  return rc;
 }
 
 extern "C" int fx_spmm_host(const fx_tiles* tc, const float* B_host, float* C_host, int k, float* total_ms,

@@ -200,6 +200,9 @@ struct fx_tiles {
   fx_flex_dev flex;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned long long* stats_host = nullptr;  // pinned mirror of aspt.stats
+  // fx_axw: the intermediate factor (X*W, or A*X)
+  float* axw_scratch = nullptr;
+  size_t axw_cap = 0;
   // host staging for fx_spmm_host
   float *B_stage_dev = nullptr, *C_stage_dev = nullptr;
   float *B_pinned = nullptr, *C_pinned = nullptr;
@@ -234,6 +237,7 @@ int spmm_csr(const uint32_t* rowptr, const uint32_t* col, const float* val, int6
 // width > 0: compute only `width` feature columns starting at the B / C pointers (row stride stays k)
 int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s, int width = 0);
 int spmm_aspt_times(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s, float ms[4]);
+int gemm_xw(const float* X, const float* W, float* out, int64_t rows, int k, int c, cudaStream_t s);
 int permute_rows(const int32_t* map, int64_t n, int k, const float* src, float* dst, bool scatter,
                  cudaStream_t s);
 }  // namespace fx

@@ -19,6 +19,7 @@
 
 #include "fx_common.cuh"
 #include "fx_tc_kernel.cuh"
+#include "fx_gemm_kernel.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -768,6 +769,26 @@ int spmm_aspt_times(const fx_tiles* t, const float* B, float* C, int k, cudaStre
   for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
   if (out == FX_ERR_CUDA && rc == FX_OK) set_error("fx_spmm_kernel_times: event timing failed: %s", cudaGetErrorString(cudaGetLastError()));
   return out;
+}
+
+template <int N>
+static int launch_gemm(const fxtc::GemmArgs& g, cudaStream_t s) {
+  const size_t smem = fxtc::gemm_smem_bytes<N>();
+  static SmemAttr attr;
+  if (int rc = attr.ensure(fxtc::k_gemm_xw<N>, smem)) return rc;
+  dim3 grid(ceil_div(g.rows, fxtc::TC_BH), ceil_div(g.c, N));
+  fxtc::k_gemm_xw<N><<<grid, 256, smem, s>>>(g);
+  FX_LAUNCH_CHECK();
+  return FX_OK;
+}
+
+// out[rows x c] = X[rows x k] * W[k x c] on tcgen05 (3xTF32), fx_gemm_kernel.cuh
+int gemm_xw(const float* X, const float* W, float* out, int64_t rows, int k, int c, cudaStream_t s) {
+  if (rows == 0) return FX_OK;
+  FX_REQUIRE(k % 4 == 0 && c % 4 == 0 && k > 0 && c > 0, FX_ERR_UNSUPPORTED, "AXW: k and c must be multiples of 4");
+  fxtc::GemmArgs g{X, W, out, (int)rows, k, c};
+  const int N = c <= 32 ? 32 : (c <= 64 ? 64 : 128);
+  return N == 32 ? launch_gemm<32>(g, s) : (N == 64 ? launch_gemm<64>(g, s) : launch_gemm<128>(g, s));
 }
 
 int permute_rows(const int32_t* map, int64_t n, int k, const float* src, float* dst, bool scatter, cudaStream_t s) {

@@ -231,6 +231,15 @@ int fx_spmm_kernel_times(const fx_tiles *t, const float *B_dev, float *C_dev, in
 int fx_spmm_host(const fx_tiles *t, const float *B_host, float *C_host, int k, float *total_ms,
                  float *tElap_ms);
 
+/* ---- L3a: AXW, the GCN layer product (cusp.cu:3-208 run1 / run2, main.cu:22-79; dead code in the reference) ----------
+ * X [n x k], W [k x c], C [rows x c], all row-major fp32 on the device.  order 0: C = A*(X*W) (run1: the dense factor
+ * first, then the SpMM at width c); order 1: C = (A*X)*W (run2).  The dense factor runs on tcgen05 with the 3xTF32 split
+ * (fp32 accuracy); the intermediate lives in a scratch of the handle.  k and c multiples of 4; with ASpT / tensor-window
+ * tiles c (order 0) resp. k (order 1) must not exceed the build's k, else the SpMM takes the CSR kernel.  gemm_ms / spmm_ms
+ * (optional) receive the two device times and make the call wait. */
+int fx_axw(const fx_tiles *t, const float *X_dev, const float *W_dev, float *C_dev, int k, int c, int order, void *stream,
+           float *gemm_ms, float *spmm_ms);
+
 /* ---- L3b: row-panel sharded SpMM from host buffers (the reference is single-GPU: no counterpart) ------
  * One process per GPU.  Every rank builds the tiles of ITS row-panel shard (fx_build with row_begin/row_end; B is
  * replicated, no collective is on the multiply itself).  What a G-rank job must not do is push all of B through the
