@@ -27,7 +27,14 @@ struct fx_flex_dev {
   int *next_seg = nullptr, *grouped_tailSeg = nullptr;
   unsigned* counter = nullptr;
   int nsegs = 0, rows_total = 0, seg_cap = 0;
-  bool pillar_owned = false;
+  // pillar builder (fx_flex_build.cu, rounds 2-3 of csr2_DiagTiling on the GPU)
+  unsigned char* listed = nullptr;            // [m]   column seen inside a diagonal block in round 1
+  int* pstart = nullptr;                      // [partitions+1] first row of every diagonal block
+  int *nzcnt = nullptr, *nzoff = nullptr;     // per row panel: nz left for round 3 and their exclusive scan
+  int* perr = nullptr;                        // error flags of the device rounds
+  void* scan_tmp = nullptr;
+  size_t scan_tmp_bytes = 0;
+  int partitions = 0, r2_nnz = 0;
   PillarHost ph;
   std::vector<int> h_count, h_next, h_tail;
   // host copies handed out by the export calls

@@ -2,7 +2,7 @@
 //
 //   FX_FMT_TILE   csr2flex_Rmajor / csr2flex_Cmajor   mat.cu:1345-1518   GPU builder
 //   FX_FMT_SEG    csr2seg_Cmajor + SM buckets         mat.cu:1192-1269, 1118-1162   GPU builder
-//   FX_FMT_PILLAR csr2_DiagTiling                     mat.cu:680-903    host round 1-2 + GPU-free round 3
+//   FX_FMT_PILLAR csr2_DiagTiling                     mat.cu:680-903    host round 1 (serial chain) + GPU rounds 2-3
 //
 // GPU builders: one cooperative tile of TM lanes per row panel, lane i owning row i's cursor; a step
 // of the reference's sequential sweep (next flexible-origin tile / next distinct column) becomes a
@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 #include <cooperative_groups/reduce.h>
 #include <cooperative_groups/scan.h>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <numeric>
@@ -148,6 +149,153 @@ __global__ void k_seg_tail(SegOut o, int nsegs, int rows_total, unsigned nnz) {
   o.pillar_rowPtr[nsegs] = (unsigned)rows_total;
   o.segPtr[nsegs] = nnz;
 }
+
+// ---------------------------------------------------------------------------------------------
+// F5: pillar format, rounds 2 and 3 of csr2_DiagTiling (mat.cu:771-903)
+// ---------------------------------------------------------------------------------------------
+// Round 1 (host, fx_flex_host.cu) leaves the diagonal blocks (pstart) and one byte per column (listed).  Round 2 gives every row
+// the nz whose column lies in the column window of the row's SM (the rows of its 64 blocks) and is listed -- independent per
+// row: one warp per row counts, a scan places, one warp per row writes.  Round 3 cuts what is left into column-major
+// segments per tm-row panel, the k_seg sweep above over a filtered row (a nz is "claimed" iff round 2 took it, so the
+// reference's per-row hash sets reduce to re-evaluating the round-2 predicate).
+struct PillarIn {
+  const unsigned *rowptr, *col;
+  const float* val;
+  const int* vo_mp;
+  const unsigned char* listed;
+  const int* pstart;  // [wpw+1] strictly increasing, pstart[wpw] == m
+  int m, wpw;
+};
+
+struct PillarOut {
+  unsigned *alpha_rowPtr, *alpha_colIdx, *pillar_rowPtr, *segVoMap;
+  float* alpha_vals;
+};
+
+// column window of the SM that owns `row` (mat.cu:773-779): the rows of the group of 64 blocks holding the row's block
+__device__ __forceinline__ void sm_window(const PillarIn& a, int row, unsigned& cs, unsigned& ce) {
+  int lo = 0, hi = a.wpw;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (a.pstart[mid] <= row) lo = mid; else hi = mid;
+  }
+  const int g = lo & ~63;
+  cs = (unsigned)a.pstart[g];
+  ce = (unsigned)a.pstart[min(g + 64, a.wpw)];
+}
+
+__device__ __forceinline__ bool r2_takes(const PillarIn& a, unsigned c, unsigned cs, unsigned ce) {
+  return c >= cs && c < ce && a.listed[c];
+}
+
+__global__ void __launch_bounds__(256) k_pillar_count(PillarIn a, PillarOut o) {
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (row > a.m) return;
+  if (row == a.m) { if (lane == 0) o.alpha_rowPtr[a.m] = 0; return; }
+  unsigned cs, ce;
+  sm_window(a, row, cs, ce);
+  const unsigned rs = a.rowptr[row], re = a.rowptr[row + 1];
+  int cnt = 0;
+  for (unsigned e = rs + lane; e < re; e += 32) cnt += r2_takes(a, a.col[e], cs, ce);
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) {
+    o.alpha_rowPtr[row] = (unsigned)cnt;  // scanned in place
+    const unsigned v = (unsigned)a.vo_mp[row];
+    o.segVoMap[row] = cnt < (int)(re - rs) ? (v | 0x80000000u) : v;  // mat.cu:826-833
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pillar_fill(PillarIn a, PillarOut o, int* __restrict__ err) {
+  const size_t gt = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (gt < (size_t)a.wpw) {  // assert( nnz_p_warp[i] ), mat.cu:835
+    if (o.alpha_rowPtr[a.pstart[gt + 1]] == o.alpha_rowPtr[a.pstart[gt]]) atomicExch(err, 1 + (int)gt);
+  }
+  const int row = (int)(gt >> 5), lane = threadIdx.x & 31;
+  if (row >= a.m) return;
+  unsigned cs, ce;
+  sm_window(a, row, cs, ce);
+  const unsigned rs = a.rowptr[row], re = a.rowptr[row + 1];
+  unsigned base = o.alpha_rowPtr[row];
+  for (unsigned e0 = rs; e0 < re; e0 += 32) {
+    const unsigned e = e0 + lane;
+    unsigned c = 0;
+    bool t = false;
+    if (e < re) { c = a.col[e]; t = r2_takes(a, c, cs, ce); }
+    const unsigned bal = __ballot_sync(0xffffffffu, t);
+    if (t) {
+      const unsigned pos = base + __popc(bal & ((1u << lane) - 1u));
+      o.alpha_colIdx[pos] = c;
+      o.alpha_vals[pos] = a.val[e];
+    }
+    base += __popc(bal);
+  }
+}
+
+// csr2seg_Cmajor (mat.cu:1192-1269) over the nz round 2 left, nnz_limit = 128 (mat.cu:875 passes the member default)
+template <int TM, bool WRITE>
+__global__ void __launch_bounds__(128) k_pseg(PillarIn a, int npanels, int nnz_limit, int* __restrict__ segs_per_panel,
+                                              int* __restrict__ nz_per_panel, const int* __restrict__ seg_off,
+                                              const int* __restrict__ nz_off, PillarOut o) {
+  auto tile = cg::tiled_partition<TM>(cg::this_thread_block());
+  const int lane = tile.thread_rank();
+  const int p = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / TM);
+  if (p >= npanels) return;
+  const int rowStart = p * TM, rowEnd = min(a.m, rowStart + TM), rows = rowEnd - rowStart;
+  const int dif = (int)(0.1 * nnz_limit);
+  const bool has_row = lane < rows;
+  const int row = rowStart + lane;
+  const unsigned rs = has_row ? a.rowptr[row] : 0, re = has_row ? a.rowptr[row + 1] : 0;
+  unsigned cs = 0, ce = 0;
+  if (has_row) sm_window(a, row, cs, ce);
+  auto skip = [&](unsigned e) {
+    while (e < re && r2_takes(a, a.col[e], cs, ce)) ++e;
+    return e;
+  };
+  unsigned cur = skip(rs), prev = cur;
+  int emitted = 0, nnzInSeg = 0, nseg = 0, atom = 0;
+  const unsigned r2 = WRITE ? o.alpha_rowPtr[a.m] : 0;
+  const int s0 = WRITE ? seg_off[p] : 0;
+  const unsigned nz0 = WRITE ? r2 + (unsigned)nz_off[p] : 0;
+  bool left = tile.any(cur < re);
+  while (left || nnzInSeg > 0) {
+    if (left) {
+      const unsigned c = cur < re ? a.col[cur] : NOCOL;
+      const unsigned j = cg::reduce(tile, c, cg::less<unsigned>());
+      const bool take = c == j;
+      if (take) { cur = skip(cur + 1); ++atom; }
+      nnzInSeg += __popc(tile.ballot(take));
+      left = tile.any(cur < re);
+    }
+    if ((!left && nnzInSeg) || (nnz_limit - nnzInSeg) <= dif || nnzInSeg > nnz_limit) {  // mat.cu:1235
+      if (WRITE) {
+        const int ex = cg::exclusive_scan(tile, atom);
+        const unsigned seg_base = nz0 + emitted;
+        const size_t rbase = (size_t)s0 * TM + (size_t)nseg * rows;  // every earlier panel has TM rows
+        if (has_row) {
+          o.alpha_rowPtr[a.m + 1 + rbase + lane] = seg_base + ex + atom;  // end of the virtual row; its start is the entry before
+          unsigned w = seg_base + ex;
+          for (unsigned e = prev; e < cur; ++e) {
+            const unsigned cc = a.col[e];
+            if (r2_takes(a, cc, cs, ce)) continue;
+            o.alpha_colIdx[w] = cc;
+            o.alpha_vals[w] = a.val[e];
+            ++w;
+          }
+          const unsigned v = (unsigned)a.vo_mp[row];
+          o.segVoMap[a.m + rbase + lane] = atom < (int)(re - rs) ? (v | 0x80000000u) : v;  // mat.cu:1252-1260
+        }
+        if (lane == 0) o.pillar_rowPtr[a.wpw + s0 + nseg] = (unsigned)(a.m + rbase);
+      }
+      emitted += nnzInSeg;
+      nnzInSeg = 0; atom = 0; prev = cur;
+      ++nseg;
+    }
+  }
+  if (!WRITE && lane == 0) { segs_per_panel[p] = nseg; nz_per_panel[p] = emitted; }
+  if (!WRITE && p == npanels - 1 && lane == 0) { segs_per_panel[npanels] = 0; nz_per_panel[npanels] = 0; }
+}
+
+__global__ void k_pillar_tail(PillarOut o, int wpw, int nsegs3, unsigned rows_total) { o.pillar_rowPtr[wpw + nsegs3] = rows_total; }
 
 // ---------------------------------------------------------------------------------------------
 // F1: flexible-origin tiles
@@ -395,8 +543,9 @@ int d2h(std::vector<T>& dst, const void* src, size_t count) {
 
 namespace fx {
 
-// ---- host round 1+2 of csr2_DiagTiling and the F4 buckets live in fx_flex_host.cu ----
-int diag_tiling_host(const fx_matrix* m, int tm, int n_sm, fx_flex_dev::PillarHost& out);
+// ---- round 1 of csr2_DiagTiling lives in fx_flex_host.cu ----
+int diag_round1_host(const fx_matrix* m, int n_sm, std::vector<int>& tile_width, int& warps_with_weights,
+                     std::vector<uint8_t>& listed);
 
 static int n_sm_of(const fx_tiles* t) {
   return t->opts.n_sm > 0 ? t->opts.n_sm : sm_count_of_current_device();
@@ -435,6 +584,19 @@ int flex_carve(fx_tiles* t) {
     add(sizeof(int) * 2 * (nnz + 2)); add(sizeof(float) * (nnz + 2)); add(sizeof(float) * 2 * (nnz + 2));
     add(sizeof(int) * rows_cap); add(sizeof(int) * ((size_t)f.seg_cap * (f.tm + 1) + 2));
     add(sizeof(int) * (f.n_sm + 2) * 2);
+  } else if (t->format == FX_FMT_PILLAR) {
+    f.partitions = 64 * f.n_sm;  // warps_per_sm * n_sm, mat.cu:688-700
+    f.seg_cap = (int)(nnz / (128 - 12) + f.npanels + 2);  // round 3: every cut but the last of a panel holds >= 116 nz
+    const size_t rows_cap = (size_t)n + 1 + (size_t)f.seg_cap * f.tm + 2;
+    add(sizeof(int) * (f.npanels + 2) * 2);   // nzcnt, nzoff
+    add((size_t)n + 4); add(sizeof(int) * (f.partitions + 2));   // listed, pstart
+    add(sizeof(int) * rows_cap); add(sizeof(int) * rows_cap);     // alpha_rowPtr, segVoMap
+    add(sizeof(int) * (nnz + 2)); add(sizeof(float) * (nnz + 2)); // alpha_colIdx, alpha_vals
+    add(sizeof(int) * ((size_t)f.partitions + f.seg_cap + 2));    // pillar_rowPtr
+    add(sizeof(int) * (f.n_sm + 2)); add(sizeof(int) * (f.n_sm + 1) * 16); add(sizeof(int) * 4);  // pillarIdx, counter, perr
+    f.scan_tmp_bytes = 0;
+    FX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, f.scan_tmp_bytes, (int*)nullptr, (int*)nullptr, (int)std::max<int64_t>(n + 1, f.npanels + 1)));
+    add(f.scan_tmp_bytes);
   }
   int rc = t->arena.reserve(bytes + 1024);
   if (rc != FX_OK) return rc;
@@ -457,6 +619,16 @@ int flex_carve(fx_tiles* t) {
     f.segVoMapPad = A.take<unsigned>(rows_cap); f.seg_rowPtr = A.take<int>((size_t)f.seg_cap * (f.tm + 1) + 2);
     f.next_seg = A.take<int>(f.n_sm + 2); f.grouped_tailSeg = A.take<int>(f.n_sm + 2);
     if (!f.grouped_tailSeg) { set_error("arena overflow"); return FX_ERR_NOMEM; }
+  } else if (t->format == FX_FMT_PILLAR) {
+    const size_t rows_cap = (size_t)n + 1 + (size_t)f.seg_cap * f.tm + 2;
+    f.nzcnt = A.take<int>(f.npanels + 2); f.nzoff = A.take<int>(f.npanels + 2);
+    f.listed = A.take<unsigned char>(n + 4); f.pstart = A.take<int>(f.partitions + 2);
+    f.alpha_rowPtr = A.take<unsigned>(rows_cap); f.segVoMap = A.take<unsigned>(rows_cap);
+    f.alpha_colIdx = A.take<unsigned>(nnz + 2); f.alpha_vals = A.take<float>(nnz + 2);
+    f.pillar_rowPtr = A.take<unsigned>((size_t)f.partitions + f.seg_cap + 2);
+    f.pillarIdx = A.take<unsigned>(f.n_sm + 2); f.counter = A.take<unsigned>((f.n_sm + 1) * 16); f.perr = A.take<int>(4);
+    f.scan_tmp = A.take<char>(f.scan_tmp_bytes);
+    if (!f.scan_tmp) { set_error("arena overflow"); return FX_ERR_NOMEM; }
   }
   return FX_OK;
 }
@@ -550,29 +722,71 @@ int flex_build(fx_tiles* t, cudaStream_t s) {
     return FX_OK;
   }
   if (t->format == FX_FMT_PILLAR) {
-    // Round 1 of csr2_DiagTiling grows the diagonal blocks one row at a time, each block starting
-    // where the previous one ended (mat.cu:706-759): a serial dependence over the whole diagonal, so
-    // -- like the reference -- this format is built on the host and uploaded (it is inside tPre).
-    int rc = diag_tiling_host(t->mat, f.tm, f.n_sm, f.ph);
+    // Round 1 of csr2_DiagTiling grows the diagonal blocks one row at a time, each block starting where the previous one ended
+    // (mat.cu:706-759): a serial dependence over the whole diagonal, kept on the host (inside tPre, like the reference's
+    // whole builder).  Rounds 2 and 3 run here on the GPU from the block boundaries and one byte per column.
+    const fx_matrix* m = t->mat;
+    std::vector<int> tile_width;
+    std::vector<uint8_t> listed;
+    int wpw = 0;
+    int rc = diag_round1_host(m, f.n_sm, tile_width, wpw, listed);
     if (rc) return rc;
+    std::vector<int> pstart(wpw + 1, 0);
+    for (int i = 0; i < wpw; ++i) pstart[i + 1] = pstart[i] + tile_width[i];
+    FX_REQUIRE(pstart[wpw] == f.m, FX_ERR_FORMAT, "diagonal blocks do not cover every row (assert mat.cu:853)");
+    FX_CUDA(cudaMemcpyAsync(f.listed, listed.data(), (size_t)f.m, cudaMemcpyHostToDevice, s));
+    FX_CUDA(cudaMemcpyAsync(f.pstart, pstart.data(), sizeof(int) * (wpw + 1), cudaMemcpyHostToDevice, s));
+    FX_CUDA(cudaMemcpyAsync(f.pillar_rowPtr, pstart.data(), sizeof(int) * (wpw + 1), cudaMemcpyHostToDevice, s));
+    FX_CUDA(cudaMemsetAsync(f.perr, 0, sizeof(int) * 4, s));
+    PillarIn in{m->rowptr_dev, m->col_dev, m->val_dev, m->vo_mp_dev, f.listed, f.pstart, f.m, wpw};
+    PillarOut o{f.alpha_rowPtr, f.alpha_colIdx, f.pillar_rowPtr, f.segVoMap, f.alpha_vals};
+    // round 2 (mat.cu:771-835)
+    const int rgrid = ceil_div(((long long)f.m + 1) * 32, 256);
+    k_pillar_count<<<rgrid, 256, 0, s>>>(in, o);
+    FX_LAUNCH_CHECK();
+    FX_CUDA(cub::DeviceScan::ExclusiveSum(f.scan_tmp, f.scan_tmp_bytes, (int*)f.alpha_rowPtr, (int*)f.alpha_rowPtr, f.m + 1, s));
+    k_pillar_fill<<<rgrid, 256, 0, s>>>(in, o, f.perr);
+    FX_LAUNCH_CHECK();
+    // round 3 (mat.cu:871-878): what is left, as column-major segments per tm-row panel, into the shared balance queue
+    const int threads = 128;
+    const int grid = ceil_div((long long)f.npanels * f.tm, threads);
+#define FX_PSEG(TM, W) k_pseg<TM, W><<<grid, threads, 0, s>>>(in, f.npanels, 128, f.count, f.nzcnt, f.off, f.nzoff, o)
+    switch (f.tm) { case 2: FX_PSEG(2, false); break; case 4: FX_PSEG(4, false); break; case 8: FX_PSEG(8, false); break; default: FX_PSEG(16, false); }
+    FX_LAUNCH_CHECK();
+    FX_CUDA(cub::DeviceScan::ExclusiveSum(f.scan_tmp, f.scan_tmp_bytes, f.count, f.off, f.npanels + 1, s));
+    FX_CUDA(cub::DeviceScan::ExclusiveSum(f.scan_tmp, f.scan_tmp_bytes, f.nzcnt, f.nzoff, f.npanels + 1, s));
+    switch (f.tm) { case 2: FX_PSEG(2, true); break; case 4: FX_PSEG(4, true); break; case 8: FX_PSEG(8, true); break; default: FX_PSEG(16, true); }
+#undef FX_PSEG
+    FX_LAUNCH_CHECK();
+    int* sh = reinterpret_cast<int*>(t->stats_host);
+    FX_CUDA(cudaMemcpyAsync(sh + 0, f.off + f.npanels, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaMemcpyAsync(sh + 1, f.count + (f.npanels - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaMemcpyAsync(sh + 2, f.alpha_rowPtr + f.m, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaMemcpyAsync(sh + 3, f.nzoff + f.npanels, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaMemcpyAsync(sh + 4, f.perr, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaStreamSynchronize(s));
+    const int nsegs3 = sh[0], last_cnt = sh[1];
+    f.r2_nnz = sh[2];
+    FX_REQUIRE(sh[4] == 0, FX_ERR_FORMAT, "pillar %d without nz (assert mat.cu:835)", sh[4] - 1);
+    FX_REQUIRE(f.r2_nnz + sh[3] == f.nnz, FX_ERR_FORMAT, "pillar format lost nz (assert mat.cu:895)");
+    FX_REQUIRE(nsegs3 <= f.seg_cap, FX_ERR_FORMAT, "pillar format: more balance segments than reserved");
+    const int last_rows = f.m - (f.npanels - 1) * f.tm;
+    f.rows_total = f.m + nsegs3 * f.tm - last_cnt * (f.tm - last_rows);
+    f.nsegs = wpw + nsegs3;
+    k_pillar_tail<<<1, 1, 0, s>>>(o, wpw, nsegs3, (unsigned)f.rows_total);
+    FX_LAUNCH_CHECK();
     auto& P = f.ph;
-    f.rows_total = (int)P.alpha_rowPtr.size() - 1;
-    f.nsegs = P.n_segs;
-    auto up = [&](auto*& dptr, const auto& v) -> int {
-      using T = typename std::remove_reference<decltype(v)>::type::value_type;
-      if (dptr) cudaFree(dptr);
-      dptr = nullptr;
-      FX_CUDA(cudaMalloc(&dptr, sizeof(T) * std::max<size_t>(v.size(), 1)));
-      FX_CUDA(cudaMemcpyAsync(dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, s));
-      return FX_OK;
-    };
-    if ((rc = up(f.alpha_rowPtr, P.alpha_rowPtr)) || (rc = up(f.alpha_colIdx, P.alpha_colIdx)) ||
-        (rc = up(f.alpha_vals, P.alpha_vals)) || (rc = up(f.pillar_rowPtr, P.alpha_pillar_rowPtr)) ||
-        (rc = up(f.pillarIdx, P.alpha_pillarIdx)) || (rc = up(f.segVoMap, P.segVoMap)))
-      return rc;
-    if (f.counter) cudaFree(f.counter);
-    FX_CUDA(cudaMalloc(&f.counter, sizeof(unsigned) * (f.n_sm + 1) * 16));
-    f.pillar_owned = true;
+    P = fx_flex_dev::PillarHost();
+    for (int i = 0; i < wpw; i += 64) P.alpha_pillarIdx.push_back((unsigned)i);              // mat.cu:831-833
+    while ((int)P.alpha_pillarIdx.size() <= f.n_sm) P.alpha_pillarIdx.push_back((unsigned)wpw);  // mat.cu:835
+    P.alpha_pillarIdx.push_back((unsigned)f.nsegs);                                          // mat.cu:881
+    FX_REQUIRE((int)P.alpha_pillarIdx.size() == f.n_sm + 2, FX_ERR_FORMAT, "alpha_pillarIdx has %zu entries (assert mat.cu:899)", P.alpha_pillarIdx.size());
+    P.n_segs = f.nsegs;
+    P.warps_with_weights = wpw;
+    P.empty_wp_p = (1 - (float)wpw / f.partitions) * 100;
+    P.band_nz_p = (float)f.r2_nnz / m->rowptr[f.m] * 100;
+    FX_CUDA(cudaMemcpyAsync(f.pillarIdx, P.alpha_pillarIdx.data(), sizeof(unsigned) * (f.n_sm + 2), cudaMemcpyHostToDevice, s));
+    FX_CUDA(cudaStreamSynchronize(s));
     return FX_OK;
   }
   set_error("flex_build: unknown format");
@@ -621,13 +835,7 @@ int flex_spmm(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
   return FX_OK;
 }
 
-void flex_release(fx_tiles* t) {
-  fx_flex_dev& f = t->flex;
-  if (f.pillar_owned) {
-    cudaFree(f.alpha_rowPtr); cudaFree(f.alpha_colIdx); cudaFree(f.alpha_vals); cudaFree(f.pillar_rowPtr);
-    cudaFree(f.pillarIdx); cudaFree(f.segVoMap); cudaFree(f.counter);
-  }
-}
+void flex_release(fx_tiles*) {}  // every array of the Flex formats lives in the handle's arena
 
 }  // namespace fx
 
@@ -674,6 +882,13 @@ extern "C" int fx_tiles_export_pillar(fx_tiles* t, fx_pillar_arrays* o) {
   FX_REQUIRE(t && o && t->format == FX_FMT_PILLAR, FX_ERR_ARG, "fx_tiles_export_pillar: not a pillar-format handle");
   fx_flex_dev& f = t->flex;
   auto& P = f.ph;
+  FX_CUDA(cudaDeviceSynchronize());
+  int rc;
+  const size_t R = f.rows_total, S = f.nsegs, N = f.nnz;
+  if ((rc = d2h(P.alpha_rowPtr, f.alpha_rowPtr, R + 1)) || (rc = d2h(P.alpha_colIdx, f.alpha_colIdx, N)) ||
+      (rc = d2h(P.alpha_pillar_rowPtr, f.pillar_rowPtr, S + 1)) || (rc = d2h(P.segVoMap, f.segVoMap, R)) ||
+      (rc = d2h(P.alpha_vals, f.alpha_vals, N)))
+    return rc;
   o->m = f.m; o->nnz = f.nnz; o->n_sm = f.n_sm; o->n_segs = P.n_segs; o->rows_total = f.rows_total;
   o->warps_with_weights = P.warps_with_weights;
   o->alpha_rowPtr = P.alpha_rowPtr.data(); o->alpha_colIdx = P.alpha_colIdx.data();

@@ -70,3 +70,27 @@ def test_tile_word_is_a_bijection():
     # K-major core matrices: 4 consecutive k of one row are 4 consecutive words, 8 rows of a core matrix 16 B apart
     assert tcw.tile_word(5, 1) - tcw.tile_word(5, 0) == 1 and tcw.tile_word(6, 0) - tcw.tile_word(5, 0) == 4
     assert tcw.tile_word(0, 4) - tcw.tile_word(0, 0) == 32 and tcw.tile_word(8, 0) - tcw.tile_word(0, 0) == 256
+
+
+def test_shard_gate_scales_with_the_nz_share():
+    """A row-panel shard answers the whole-matrix gate for its share of the nz (fx_api.cu fx_build, oracle/tcw.py plan):
+    halves of a matrix whose windows pay keep theirs; with the absolute threshold neither half would."""
+    n = 2048
+    rp, c, v = random_csr(n, 9, 7, hubs=1, blocks=12)
+    whole = tcw.plan(rp, c, v, min_total=0)
+    gate = whole["net_gain"]                       # the whole matrix passes exactly at its own gain
+    assert tcw.plan(rp, c, v, min_total=gate)["ntc"] == whole["ntc"] > 0
+    assert tcw.plan(rp, c, v, min_total=gate + 1)["ntc"] == 0
+    mid = 1024
+    halves = [tcw.plan(rp, c, v, min_total=0, row_begin=a, row_end=b) for a, b in ((0, mid), (mid, n))]
+    assert sum(h["net_gain"] for h in halves) == whole["net_gain"]     # panels are independent
+    nnz = int(rp[-1])
+    for (a, b), h in zip(((0, mid), (mid, n)), halves):
+        share = int(rp[b]) - int(rp[a])
+        scaled = gate * share // nnz
+        got = tcw.plan(rp, c, v, min_total=gate, row_begin=a, row_end=b)
+        assert (got["ntc"] > 0) == (h["net_gain"] >= scaled)
+        # the same shard against an UNscaled threshold (what round 1 did) would drop its windows whenever its own gain is
+        # below the whole matrix's -- which is always, for a proper shard of a matrix with windows in both halves
+        assert h["net_gain"] < gate
+    assert any(tcw.plan(rp, c, v, min_total=gate, row_begin=a, row_end=b)["ntc"] > 0 for a, b in ((0, mid), (mid, n)))
