@@ -233,7 +233,9 @@ def e2e_sharded(dist, fx, mat, Bh, Ch, n, k, lo, hi, rank, world, dev, steps, sy
         comm = fx.Comm(world, rank, bcast)
         slo, shi = comm.slice(n)
         Bslice = Bh.numpy()[slo:shi]
-        Ch2 = torch.empty((hi - lo, k), dtype=torch.float32).pin_memory()
+        Ch2 = torch.empty((hi - lo, k), dtype=torch.float32)
+        if dev.type == "cuda":
+            Ch2 = Ch2.pin_memory()
         for _ in range(2):
             comm.spmm_sharded_host(mat, Bslice, Ch2.numpy())
         # same kernels and the same column chunks as fx_spmm_host: the results must agree closely

@@ -73,18 +73,39 @@ def _worker_host(rank, world, port, ret):
 
 
 class _CpuMat:
-    """Stand-in for flex_b200.Mat on the CPU ranks: spmm(B_ptr, C_ptr, k) over raw pointers, through the oracle."""
+    """Stand-in for flex_b200.Mat on the CPU ranks: the shard's multiply through the oracle."""
 
     def __init__(self, sub, c, v, n, rows):
         self.sub, self.c, self.v, self.n, self.rows = sub, c, v, n, rows
 
-    def spmm(self, B_ptr, C_ptr, k, stream=None):
-        import ctypes
-        from oracle import orc
-        Bf = np.ctypeslib.as_array(ctypes.cast(B_ptr, ctypes.POINTER(ctypes.c_float)), shape=(self.n, k))
-        if self.rows:
-            Cl = np.ctypeslib.as_array(ctypes.cast(C_ptr, ctypes.POINTER(ctypes.c_float)), shape=(self.rows, k))
-            Cl[:] = orc.spmm_ref(self.sub, self.c, self.v, np.ascontiguousarray(Bf))
+
+class _CpuFx:
+    """Stand-in for the `flex_b200` module in bench.e2e_sharded: `Comm` with the surface of flex_b200.Comm (the C entry
+    fx_spmm_sharded_host over NCCL), here flex_b200.shard.ShardedHostSpmm over gloo with the oracle as the multiply."""
+
+    class Comm:
+        def __init__(self, nranks, rank, broadcast_bytes):
+            assert broadcast_bytes(b"id" if rank == 0 else None) == b"id"   # the ncclUniqueId hand-over
+            self.nranks, self.rank, self.run = nranks, rank, None
+
+        def slice(self, n):
+            per = (n + self.nranks - 1) // self.nranks
+            lo = min(n, self.rank * per)
+            return lo, min(n, lo + per)
+
+        def spmm_sharded_host(self, mat, B_rows, C_local):
+            from flex_b200.shard import ShardedHostSpmm
+            from oracle import orc
+            k = C_local.shape[1]
+            if self.run is None:
+                def spmm(B_full, C_out):
+                    if mat.rows:
+                        C_out.copy_(torch.from_numpy(orc.spmm_ref(mat.sub, mat.c, mat.v, np.ascontiguousarray(B_full.numpy()[:mat.n]))))
+                self.run = ShardedHostSpmm(dist, mat.n, k, self.rank, self.nranks, torch.device("cpu"), spmm, mat.rows)
+            self.run(torch.from_numpy(np.ascontiguousarray(B_rows)), torch.from_numpy(C_local))
+
+        def free(self):
+            self.run = None
 
 
 def _worker_bench(rank, world, port, ret):
@@ -103,8 +124,8 @@ def _worker_bench(rank, world, port, ret):
     cs, vs = c[rp[lo]:rp[hi]], v[rp[lo]:rp[hi]]
     mat = _CpuMat(sub, cs, vs, n, hi - lo)
     Ch = torch.from_numpy(orc.spmm_ref(sub, cs, vs, B) if hi > lo else np.zeros((0, k), np.float32))
-    ms, h2d, note = bench.e2e_sharded(dist, mat, torch.from_numpy(B), Ch, n, k, lo, hi, rank, world, torch.device("cpu"), 2,
-                                      dist.barrier)
+    ms, h2d, note = bench.e2e_sharded(dist, _CpuFx, mat, torch.from_numpy(B), Ch, n, k, lo, hi, rank, world, torch.device("cpu"),
+                                      2, dist.barrier)
     if rank == 0:
         ret.put((ms, h2d, note))
     dist.barrier()
