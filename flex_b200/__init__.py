@@ -410,7 +410,7 @@ class Mat:
         a = PillarArrays()
         _ck(lib().fx_tiles_export_pillar(self._h, C.byref(a)))
         R, nnz = a.rows_total, a.nnz
-        return dict(n_segs=a.n_segs, rows_total=R, warps_with_weights=a.warps_with_weights,
+        return dict(n_segs=a.n_segs, rows_total=R, warps_with_weights=a.warps_with_weights, n_sm=a.n_sm,
                     empty_wp_p=a.empty_wp_p, band_nz_p=a.band_nz_p,
                     alpha_rowPtr=_np(a.alpha_rowPtr, R + 1, np.uint32).copy(),
                     alpha_colIdx=_np(a.alpha_colIdx, nnz, np.uint32).copy(),

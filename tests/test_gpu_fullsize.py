@@ -117,3 +117,62 @@ def test_named_shape_tensor_windows(orc, name, k):
         assert np.array_equal(sub["win_code"], e["win_code"][:sub["win_nnz"]])
         assert np.array_equal(sub["win_val"], e["win_val"][:sub["win_nnz"]])
     mat.free()
+
+
+@pytest.mark.parametrize("name,k,fmt,order", [("flickr", 128, "pillar", None), ("flickr", 128, "seg", None), ("flickr", 128, "tile", None),
+                                              ("flickr", 32, "pillar", "rcm"), ("reddit", 128, "pillar", None)])
+def test_flex_formats_full_size(orc, name, k, fmt, order):
+    """K2 at BASELINE shapes: the tile / tile-segment / pillar builders and their consumers on a whole flickr- / Reddit-shape
+    graph (the pillar builder's rounds 2-3 run on the GPU, fx_flex_build.cu): sampled rows against the CPU oracle in the
+    ORIGINAL order, checksum of checksums, and the format's conservation invariants."""
+    import torch
+    rp, c, v = synth.generate(name, device="cuda")
+    n, nnz = rp.numel() - 1, c.numel()
+    rph, ch, vh = rp.cpu().numpy().astype(np.uint32), c.cpu().numpy().astype(np.uint32), v.cpu().numpy()
+    dl = fx.DataLoader.from_arrays(rph, ch, vh, k, name + ".csv")
+    if order:
+        dl = dl.reorder({"rcm": fx.FX_ORDER_RCM, "deg": fx.FX_ORDER_DEG}[order])
+    mat = fx.Mat(dl, fmt=fmt, tm=4, tn=4)
+    B = synth.dense_B(n, k, device="cuda")
+    S = B
+    if order:  # kernels of a reordered loader read shadow_b and write C[voMp[row]] (flex.cu:276, :994)
+        S = torch.empty_like(B)
+        dl.permute_rows(B.data_ptr(), S.data_ptr(), k)
+    C1 = torch.full((n, k), float("nan"), device="cuda")
+    mat.spmm(S.data_ptr(), C1.data_ptr(), k)
+    torch.cuda.synchronize()
+    assert torch.isfinite(C1).all()
+    rng = np.random.default_rng(4)
+    deg = np.diff(rph.astype(np.int64))
+    rows = np.unique(np.concatenate([rng.integers(0, n, 3000), np.argsort(deg)[-16:], [0, n - 1]])).astype(np.int64)
+    gold = orc.spmm_rows(rows, rph, ch, vh, B.cpu().numpy())
+    got = C1[torch.from_numpy(rows).cuda()].cpu().numpy()
+    sub_rp = np.concatenate([[0], np.cumsum(deg[rows])]).astype(np.uint32)
+    e = orc.check(gold, got, sub_rp)
+    assert e["flex_count"] == 0 and e["aspt_pct"] < 0.01 and e["tight_count"] == 0, e
+    colsum_A = torch.zeros(n, dtype=torch.float64, device="cuda").index_add_(0, c, v.double())
+    lhs, rhs = C1.double().sum(0), colsum_A @ B.double()
+    scale = (colsum_A.abs() @ B.double().abs()).clamp_min(1.0)
+    assert ((lhs - rhs).abs() / scale).max().item() < 1e-5
+    if fmt == "pillar":  # conservation of csr2_DiagTiling's output (asserts of mat.cu:853, :895-903)
+        p = mat.export_pillar()
+        R, S_ = p["rows_total"], p["n_segs"]
+        arp, pr, pi = p["alpha_rowPtr"].astype(np.int64), p["alpha_pillar_rowPtr"].astype(np.int64), p["alpha_pillarIdx"].astype(np.int64)
+        assert arp[0] == 0 and arp[-1] == nnz and np.all(np.diff(arp) >= 0) and len(arp) == R + 1
+        assert pr[0] == 0 and pr[-1] == R and np.all(np.diff(pr) > 0) and len(pr) == S_ + 1
+        assert len(pi) == p["n_sm"] + 2 and pi[-1] == S_ and np.all(np.diff(pi) >= 0) and pr[p["warps_with_weights"]] == n
+        # every nz exactly once: (original row, column, value) multiset equals the CSR's
+        vo = (p["segVoMap"] & 0x7fffffff).astype(np.int64)
+        row_of = np.repeat(vo, np.diff(arp))
+        key = row_of * n + p["alpha_colIdx"].astype(np.int64)
+        cur_rp, cur_c, cur_v = dl.host_csr()
+        orig_rows = np.repeat(np.asarray(dl.vo_mp, np.int64) if order else np.arange(n), np.diff(cur_rp.astype(np.int64)))
+        key0 = orig_rows * n + cur_c.astype(np.int64)
+        o1, o0 = np.argsort(key, kind="stable"), np.argsort(key0, kind="stable")
+        assert np.array_equal(key[o1], key0[o0]) and np.array_equal(p["alpha_vals"][o1], np.asarray(cur_v)[o0])
+        # a row is flagged for atomic accumulation iff it is split over several pillar rows
+        multi = np.bincount(vo, minlength=n) > 1
+        flagged = np.zeros(n, bool)
+        np.logical_or.at(flagged, vo, (p["segVoMap"] >> 31).astype(bool))
+        assert np.array_equal(multi, flagged)
+    mat.free()
