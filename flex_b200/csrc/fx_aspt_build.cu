@@ -415,11 +415,6 @@ __global__ void k_nodense(const int* __restrict__ csr_v, int npanel, int nr, int
 }
 
 // ---- K5: special lists (make_special :1076-1087) in canonical (row-ascending) order ---------
-__global__ void __launch_bounds__(1024) k_scan_spec(const int* __restrict__ spec_cnt, int nr,
-                                                    int* __restrict__ spec_off) {
-  fx::cta_exclusive_scan(spec_cnt, nr, spec_off);
-}
-
 __global__ void k_fill_special(const int* __restrict__ spec_cnt, const int* __restrict__ spec_off, int nr,
                                int* __restrict__ special, int* __restrict__ special2) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -500,6 +495,7 @@ int aspt_carve(fx_tiles* t, int64_t ncols, size_t extra_bytes) {
   add(sizeof(int) * (size_t)a.special_cap * 4);  // spec_order, spec_iota, spec_keys, spec_keys_out
   cub::DeviceRadixSort::SortPairs(nullptr, a.spec_sort_tmp_bytes, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr,
                                   (int*)nullptr, a.special_cap);
+  a.spec_sort_tmp_bytes = std::max(a.spec_sort_tmp_bytes, device_scan_tmp_bytes((int)nr + 1));  // shared with the row scans
   add(a.spec_sort_tmp_bytes);
   add(sizeof(unsigned long long) * 16);
   add(sizeof(float) * a.partial_cap_floats);
@@ -594,8 +590,7 @@ int aspt_build(fx_tiles* t, cudaStream_t s) {
                                                 a.csr_e, a.csr_ev, a.spec_cnt, a.stats);
     FX_LAUNCH_CHECK();
   }
-  k_scan_spec<<<1, 1024, 0, s>>>(a.spec_cnt, a.nr, a.spec_off);
-  FX_LAUNCH_CHECK();
+  FX_CUDA(device_exclusive_scan(a.spec_sort_tmp, a.spec_sort_tmp_bytes, a.spec_cnt, a.nr, a.spec_off, s));
   k_fill_special<<<ceil_div(a.nr, 256), 256, 0, s>>>(a.spec_cnt, a.spec_off, a.nr, a.special, a.special2);
   FX_LAUNCH_CHECK();
   {  // execution order of the chunks: by the first column they read

@@ -544,8 +544,8 @@ int d2h(std::vector<T>& dst, const void* src, size_t count) {
 namespace fx {
 
 // ---- round 1 of csr2_DiagTiling lives in fx_flex_host.cu ----
-int diag_round1_host(const fx_matrix* m, int n_sm, std::vector<int>& tile_width, int& warps_with_weights,
-                     std::vector<uint8_t>& listed);
+int diag_round1_host(int M, int nnz, const uint32_t* rowptr, const uint32_t* col, int n_sm, std::vector<int>& tile_width,
+                     int& warps_with_weights, std::vector<uint8_t>& listed);
 
 static int n_sm_of(const fx_tiles* t) {
   return t->opts.n_sm > 0 ? t->opts.n_sm : sm_count_of_current_device();
@@ -728,8 +728,15 @@ int flex_build(fx_tiles* t, cudaStream_t s) {
     const fx_matrix* m = t->mat;
     std::vector<int> tile_width;
     std::vector<uint8_t> listed;
-    int wpw = 0;
-    int rc = diag_round1_host(m, f.n_sm, tile_width, wpw, listed);
+    int wpw = 0, rc = FX_OK;
+    // a matrix created from device arrays (fx_csr_from_device) has no host copy: its structure comes down once, inside tPre
+    std::vector<uint32_t> h_rowptr, h_col;
+    const uint32_t *hr = m->rowptr.data(), *hc = m->col.data();
+    if (m->col.empty() && f.nnz > 0) {
+      if ((rc = d2h(h_rowptr, m->rowptr_dev, (size_t)f.m + 1)) || (rc = d2h(h_col, m->col_dev, (size_t)f.nnz))) return rc;
+      hr = h_rowptr.data(); hc = h_col.data();
+    }
+    rc = diag_round1_host(f.m, f.nnz, hr, hc, f.n_sm, tile_width, wpw, listed);
     if (rc) return rc;
     std::vector<int> pstart(wpw + 1, 0);
     for (int i = 0; i < wpw; ++i) pstart[i + 1] = pstart[i] + tile_width[i];

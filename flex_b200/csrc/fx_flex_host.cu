@@ -12,10 +12,10 @@
 namespace fx {
 
 namespace {
-int find_col(const fx_matrix* m, int r, unsigned c) {
-  auto b = m->col.begin() + m->rowptr[r], e = m->col.begin() + m->rowptr[r + 1];
-  auto it = std::lower_bound(b, e, c);
-  return (it != e && *it == c) ? (int)(it - m->col.begin()) : -1;
+bool has_col(const uint32_t* rowptr, const uint32_t* col, int r, unsigned c) {
+  const uint32_t *b = col + rowptr[r], *e = col + rowptr[r + 1];
+  const uint32_t* it = std::lower_bound(b, e, c);
+  return it != e && *it == c;
 }
 
 }  // namespace
@@ -30,13 +30,11 @@ int find_col(const fx_matrix* m, int r, unsigned c) {
 // contain it (mat.cu:722,737: mat_r_start <= l <= j), i.e. by the SM whose window contains it, and a claimed nz always has its
 // column listed by its own block -- so inside the window "claimed or listed by s" is simply listed[l], and the reference's
 // assert at mat.cu:818 cannot fire.
-int diag_round1_host(const fx_matrix* m, int n_sm, std::vector<int>& tile_width, int& warps_with_weights,
-                     std::vector<uint8_t>& listed) {
-  FX_REQUIRE(!m->col.empty(), FX_ERR_UNSUPPORTED, "pillar format needs the host CSR");
-  const int M = (int)m->n, nnz = (int)m->nnz;
+int diag_round1_host(int M, int nnz, const uint32_t* rowptr, const uint32_t* col, int n_sm, std::vector<int>& tile_width,
+                     int& warps_with_weights, std::vector<uint8_t>& listed) {
   const int warps_per_sm = 64;   // mat.cu:688
   const float alpha = 0.3f;      // mat.cu:690
-  const int nnz_diagonal_tiles = (int)(alpha * m->rowptr[M]);
+  const int nnz_diagonal_tiles = (int)(alpha * rowptr[M]);
   const int partitions_node = warps_per_sm * n_sm;
   const int nnz_p_diagonal_tile = std::max(32, nnz_diagonal_tiles / partitions_node);
   const int thr = (int)(0.85 * nnz_p_diagonal_tile);
@@ -48,17 +46,17 @@ int diag_round1_host(const fx_matrix* m, int n_sm, std::vector<int>& tile_width,
     mat_r_start += i ? tile_width[i - 1] : 0;
     int cnt = 0, j = mat_r_start;
     while (j < M && cnt <= thr) {
-      for (unsigned kk = m->rowptr[j];; ++kk) {
+      for (unsigned kk = rowptr[j];; ++kk) {
         // the reference walks until it meets column j and does not stop at the end of the row
         // (mat.cu:718-727); running off the array is undefined there and refused here
         FX_REQUIRE(kk < (unsigned)nnz, FX_ERR_FORMAT,
                    "row %d has no diagonal entry and the reference's diagonal walk (mat.cu:718-727) leaves the matrix", j);
-        if (!(m->col[kk] <= (unsigned)j)) break;
-        if ((int)m->col[kk] >= mat_r_start) { ++cnt; listed[m->col[kk]] = 1; }
-        if (m->col[kk] == (unsigned)j) break;
+        if (!(col[kk] <= (unsigned)j)) break;
+        if ((int)col[kk] >= mat_r_start) { ++cnt; listed[col[kk]] = 1; }
+        if (col[kk] == (unsigned)j) break;
       }
       for (int kk = mat_r_start; kk < j; ++kk)
-        if (find_col(m, kk, (unsigned)j) >= 0) { ++cnt; listed[j] = 1; }
+        if (has_col(rowptr, col, kk, (unsigned)j)) { ++cnt; listed[j] = 1; }
       ++j;
     }
     warps_with_weights += cnt > 0;

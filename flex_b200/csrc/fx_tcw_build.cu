@@ -73,6 +73,32 @@ __device__ void tcw_sort_u64(unsigned long long* a, int n) {
   }
 }
 
+// The listed columns of ONE panel (at most W) in a small open-addressing table in shared memory: key = column, slot = its
+// position in the ascending list.  Pass 2 of k_tcw_select and both passes of k_tcw_split ask "is this nz's column listed, and
+// where" once per nz; through this table the question costs one or two shared-memory reads instead of a dependent global
+// load from the CTA's n-sized counter array (k_tcw_split 0.95 -> 0.xx ms on Reddit-shape).  HT = power of two >= 2 W.
+constexpr unsigned HEMPTY = 0xFFFFFFFFu;
+__host__ __device__ inline int tcw_hash_size(int W) { int h = 64; while (h < 2 * W) h <<= 1; return h; }
+__device__ __forceinline__ unsigned tcw_hash(unsigned c, int hbits) { return (c * 2654435761u) >> (32 - hbits); }
+__device__ __forceinline__ void tcw_hash_clear(unsigned* hk, int HT) {
+  for (int i = threadIdx.x; i < HT; i += blockDim.x) hk[i] = HEMPTY;
+}
+__device__ __forceinline__ void tcw_hash_insert(unsigned* hk, unsigned short* hs, int HT, int hbits, unsigned c, int slot) {
+  unsigned h = tcw_hash(c, hbits);
+  while (atomicCAS(&hk[h], HEMPTY, c) != HEMPTY) h = (h + 1) & (unsigned)(HT - 1);
+  hs[h] = (unsigned short)slot;
+}
+// MARK | slot when the column is listed, 0 otherwise
+__device__ __forceinline__ unsigned tcw_hash_find(const unsigned* hk, const unsigned short* hs, int HT, int hbits, unsigned c) {
+  unsigned h = tcw_hash(c, hbits);
+  for (;;) {
+    const unsigned k = hk[h];
+    if (k == c) return MARK | hs[h];
+    if (k == HEMPTY) return 0u;
+    h = (h + 1) & (unsigned)(HT - 1);
+  }
+}
+
 __global__ void k_tcw_pad(const uint32_t* __restrict__ rowptr, int row0, int nloc, int nr, int ne, int* __restrict__ csr_v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i <= nr) csr_v[i] = i <= nloc ? (int)(rowptr[row0 + i] - rowptr[row0]) : ne;
@@ -85,7 +111,10 @@ __global__ void __launch_bounds__(512) k_tcw_select(const int* __restrict__ csr_
                                                     int* __restrict__ tc_cols, int* __restrict__ tc_ncol,
                                                     int* __restrict__ win_len, int* __restrict__ chunk_len,
                                                     unsigned long long* __restrict__ stats) {
-  extern __shared__ unsigned long long skeys[];  // CAND_CAP
+  extern __shared__ unsigned long long skeys[];  // CAND_CAP, then the listed-column table (HT keys, HT slots)
+  const int HT = tcw_hash_size(W), hbits = 31 - __clz(HT);
+  unsigned* hk = reinterpret_cast<unsigned*>(skeys + CAND_CAP);
+  unsigned short* hs = reinterpret_cast<unsigned short*>(hk + HT);
   __shared__ int s_nc;
   __shared__ int hist[MAX_CH];
   __shared__ int s_ns;
@@ -184,7 +213,9 @@ __global__ void __launch_bounds__(512) k_tcw_select(const int* __restrict__ csr_
         for (int i = threadIdx.x; i < ns; i += blockDim.x) skeys[i] &= 0xFFFFFFFFull;  // keep the column only
         __syncthreads();
         tcw_sort_u64(skeys, ns);
-        for (int i = threadIdx.x; i < ns; i += blockDim.x) cnt[(unsigned)skeys[i]] = MARK | (unsigned)i;
+        tcw_hash_clear(hk, HT);
+        __syncthreads();
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) tcw_hash_insert(hk, hs, HT, hbits, (unsigned)skeys[i], i);
         if (threadIdx.x == 0) atomicAdd(&stats[5], (unsigned long long)captured);  // total net gain
       }
     } else if (nc > CAND_CAP && threadIdx.x == 0) {
@@ -203,7 +234,9 @@ __global__ void __launch_bounds__(512) k_tcw_select(const int* __restrict__ csr_
       for (int e0 = lb + threadIdx.x; e0 < ub; e0 += 4 * blockDim.x) {
         unsigned f[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) f[j] = e0 + j * (int)blockDim.x < ub ? cnt[col[e0 + j * (int)blockDim.x]] : 0u;
+        for (int j = 0; j < 4; ++j) f[j] = e0 + j * (int)blockDim.x < ub ? col[e0 + j * (int)blockDim.x] : HEMPTY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[j] = f[j] != HEMPTY ? tcw_hash_find(hk, hs, HT, hbits, f[j]) : 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (f[j] >> 31) {
@@ -219,9 +252,8 @@ __global__ void __launch_bounds__(512) k_tcw_select(const int* __restrict__ csr_
     for (int i = threadIdx.x; i < BH; i += blockDim.x) win_len[p * BH + i] = s_wl[i];
     __syncthreads();
     for (int i = threadIdx.x; i < CH; i += blockDim.x) chunk_len[(size_t)p * CH + i] = hist[i];
-    // only the marks have to go (they outrank every epoch); counts of this panel are stale for the next one by their epoch,
-    // and the whole scratch is cleared once at the end of the build
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) cnt[(unsigned)skeys[i]] = 0u;
+    // counts of this panel are stale for the next one by their epoch (nothing to undo), and the whole scratch is cleared
+    // once at the end of the build
     __syncthreads();
   }
 }
@@ -295,13 +327,19 @@ __global__ void __launch_bounds__(512) k_tcw_split(const int* __restrict__ csr_v
                                                    unsigned* __restrict__ cnt_all, uint16_t* __restrict__ win_code,
                                                    float* __restrict__ win_val, uint32_t* __restrict__ rest_col,
                                                    float* __restrict__ rest_val, unsigned long long* __restrict__ sched) {
-  extern __shared__ int off2[];  // [CH][128] nz of (chunk, row), then their exclusive scan
+  extern __shared__ int off2[];  // [CH][128] nz of (chunk, row), then their exclusive scan; then the listed-column table
   __shared__ int wsum[16];
   __shared__ int s_rp[BH + 1];
-  unsigned* cnt = cnt_all + (size_t)blockIdx.x * ncols;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const int CH = W / 32, n2 = CH * BH;
+  const int HT = tcw_hash_size(W), hbits = 31 - __clz(HT);
+  unsigned* hk = reinterpret_cast<unsigned*>(off2 + n2);
+  int* s_cnt = reinterpret_cast<int*>(hk + HT);  // [nwarp][CH] window nz of a step per warp and chunk (long rows)
+  int* s_run = s_cnt + nwarp * CH;               // [CH] window nz of the long row placed so far
+  unsigned short* hs = reinterpret_cast<unsigned short*>(s_run + CH);
+  __shared__ int s_rest[16], s_rrest, s_next;
+  constexpr int LONG_ROW = 512;
   __shared__ int s_panel;
   for (;;) {  // panels by a counter, as in k_tcw_select
     __syncthreads();
@@ -311,9 +349,13 @@ __global__ void __launch_bounds__(512) k_tcw_split(const int* __restrict__ csr_v
     if (p >= npanel) break;
     const int ns = tc_ncol[p];
     const int* list = tc_cols + (size_t)p * W;
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) cnt[list[i]] = MARK | (unsigned)i;
-    if (ns > 0) for (int i = threadIdx.x; i < n2; i += blockDim.x) off2[i] = 0;
+    if (ns > 0) {
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) off2[i] = 0;
+      tcw_hash_clear(hk, HT);
+    }
     for (int i = threadIdx.x; i <= BH; i += blockDim.x) s_rp[i] = csr_v[p * BH + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) tcw_hash_insert(hk, hs, HT, hbits, (unsigned)list[i], i);
     __syncthreads();
     if (ns > 0) {
       // nz of every (chunk, row): all threads stride over the panel's nz, the row of a nz comes from the panel's row pointers
@@ -321,7 +363,9 @@ __global__ void __launch_bounds__(512) k_tcw_split(const int* __restrict__ csr_v
       for (int e0 = lb + threadIdx.x; e0 < ub; e0 += 4 * blockDim.x) {
         unsigned f[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) f[j] = e0 + j * (int)blockDim.x < ub ? cnt[col[e0 + j * (int)blockDim.x]] : 0u;
+        for (int j = 0; j < 4; ++j) f[j] = e0 + j * (int)blockDim.x < ub ? col[e0 + j * (int)blockDim.x] : HEMPTY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[j] = f[j] != HEMPTY ? tcw_hash_find(hk, hs, HT, hbits, f[j]) : 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (f[j] >> 31) {
@@ -352,21 +396,87 @@ __global__ void __launch_bounds__(512) k_tcw_split(const int* __restrict__ csr_v
       __syncthreads();
     }
     const int wbase = win_cptr[(size_t)p * CH];
-    for (int r = warp; r < BH; r += nwarp) {
+    // Placing pass.  A warp per row left the CTA waiting for the warp that drew a hub row (Reddit-shape: the longest warp of a
+    // panel does 3.6 times the average work): rows of LONG_ROW nz or more are placed by the whole CTA, 32 nz per warp and
+    // step, the ranks of a step carried across warps through per-warp counts in shared memory; the other rows are handed
+    // to the warps by a counter.
+    for (int r = 0; r < BH; ++r) {
+      const int lo = s_rp[r], hi = s_rp[r + 1];
+      if (hi - lo < LONG_ROW) continue;
       const int row = p * BH + r;
-      const int lo = csr_v[row], hi = csr_v[row + 1];
+      for (int i = threadIdx.x; i < CH; i += blockDim.x) s_run[i] = 0;
+      if (threadIdx.x == 0) s_rrest = lo - win_rowptr[row];
+      unsigned c_n = 0;
+      float v_n = 0.f;
+      if (lo + (int)threadIdx.x < hi) { c_n = col[lo + threadIdx.x]; v_n = val[lo + threadIdx.x]; }
+      for (int e0 = lo; e0 < hi; e0 += (int)blockDim.x) {
+        const int e = e0 + threadIdx.x;
+        const bool valid = e < hi;
+        const unsigned c = c_n, f = (valid && ns > 0) ? tcw_hash_find(hk, hs, HT, hbits, c_n) : 0u;
+        const float v = v_n;
+        if (e + (int)blockDim.x < hi) { c_n = col[e + blockDim.x]; v_n = val[e + blockDim.x]; }
+        const bool isw = (f >> 31) != 0u;
+        const unsigned mw = __ballot_sync(0xffffffffu, isw), mr = __ballot_sync(0xffffffffu, valid && !isw);
+        for (int i = lane; i < CH; i += 32) s_cnt[warp * CH + i] = 0;
+        __syncwarp();
+        int ch = -1, sl = 0;
+        unsigned peers = 0;
+        if (isw) {
+          sl = (int)(f & 0xFFFFu);
+          ch = sl >> 5;
+          peers = __match_any_sync(mw, ch);
+          if ((peers & lt) == 0u) s_cnt[warp * CH + ch] = __popc(peers);
+        }
+        if (lane == 0) s_rest[warp] = __popc(mr);
+        __syncthreads();  // (also orders the s_run / s_rrest updates of the previous step)
+        if (isw) {
+          int rank = s_run[ch] + __popc(peers & lt);
+          for (int w2 = 0; w2 < warp; ++w2) rank += s_cnt[w2 * CH + ch];
+          const int pos = wbase + off2[ch * BH + r] + rank;
+          win_code[pos] = (uint16_t)fxtc::tile_word(r, sl & 31);
+          win_val[pos] = v;
+        } else if (valid) {
+          int pos = s_rrest + __popc(mr & lt);
+          for (int w2 = 0; w2 < warp; ++w2) pos += s_rest[w2];
+          rest_col[pos] = c;
+          rest_val[pos] = v;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < CH; i += blockDim.x) {
+          int tsum = 0;
+          for (int w2 = 0; w2 < nwarp; ++w2) tsum += s_cnt[w2 * CH + i];
+          s_run[i] += tsum;
+        }
+        if (threadIdx.x == 0) {
+          int tsum = 0;
+          for (int w2 = 0; w2 < nwarp; ++w2) tsum += s_rest[w2];
+          s_rrest += tsum;
+        }
+        __syncthreads();
+      }
+    }
+    if (threadIdx.x == 0) s_next = 0;
+    __syncthreads();
+    for (;;) {
+      int r = 0;
+      if (lane == 0) r = atomicAdd(&s_next, 1);
+      r = __shfl_sync(0xffffffffu, r, 0);
+      if (r >= BH) break;
+      const int row = p * BH + r;
+      const int lo = s_rp[r], hi = s_rp[r + 1];
+      if (hi - lo >= LONG_ROW) continue;
       int ro = lo - win_rowptr[row];
       int last_ch = -1, last_cnt = 0;
-      // the (column, value, counter) loads of the next step are requested before this step's ranks are worked out
-      unsigned c_n = 0, f_n = 0;
+      // the (column, value) loads of the next step are requested before this step's ranks are worked out
+      unsigned c_n = 0;
       float v_n = 0.f;
-      if (lo + lane < hi) { c_n = col[lo + lane]; v_n = val[lo + lane]; f_n = ns > 0 ? cnt[c_n] : 0u; }
+      if (lo + lane < hi) { c_n = col[lo + lane]; v_n = val[lo + lane]; }
       for (int e0 = lo; e0 < hi; e0 += 32) {
         const int e = e0 + lane;
         const bool valid = e < hi;
-        const unsigned c = c_n, f = valid ? f_n : 0u;
+        const unsigned c = c_n, f = (valid && ns > 0) ? tcw_hash_find(hk, hs, HT, hbits, c_n) : 0u;
         const float v = v_n;
-        if (e + 32 < hi) { c_n = col[e + 32]; v_n = val[e + 32]; f_n = ns > 0 ? cnt[c_n] : 0u; }
+        if (e + 32 < hi) { c_n = col[e + 32]; v_n = val[e + 32]; }
         const bool isw = (f >> 31) != 0u;
         const unsigned mw = __ballot_sync(0xffffffffu, isw), mr = __ballot_sync(0xffffffffu, valid && !isw);
         int ch = -1, pc = 0;
@@ -393,8 +503,6 @@ __global__ void __launch_bounds__(512) k_tcw_split(const int* __restrict__ csr_v
         }
       }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) cnt[list[i]] = 0u;
     __syncthreads();
   }
 }
@@ -459,8 +567,10 @@ int tcw_build(fx_tiles* t, cudaStream_t s) {
   k_tcw_pad<<<ceil_div(a.nr + 1, 256), 256, 0, s>>>(m->rowptr_dev, t->row_begin, nloc, a.nr, ne, w.csr_v);
   FX_LAUNCH_CHECK();
   static SmemAttr select_attr;
-  if (int rc = select_attr.ensure(k_tcw_select, CAND_CAP * sizeof(unsigned long long))) return rc;
-  k_tcw_select<<<a.G, 512, CAND_CAP * sizeof(unsigned long long), s>>>(w.csr_v, col, a.npanel, (int)m->n, w.T, w.W, w.min_gain,
+  const size_t hash_bytes = (size_t)tcw_hash_size(w.W) * (sizeof(unsigned) + sizeof(unsigned short));
+  const size_t select_smem = CAND_CAP * sizeof(unsigned long long) + hash_bytes;
+  if (int rc = select_attr.ensure(k_tcw_select, select_smem)) return rc;
+  k_tcw_select<<<a.G, 512, select_smem, s>>>(w.csr_v, col, a.npanel, (int)m->n, w.T, w.W, w.min_gain,
                                                                       w.chunk_cost, a.cnt_scratch, w.tc_cols, w.tc_ncol, w.win_len, w.chunk_len, w.stats);
   FX_LAUNCH_CHECK();
   {
@@ -469,15 +579,14 @@ int tcw_build(fx_tiles* t, cudaStream_t s) {
                                                      w.chunk_len);
     FX_LAUNCH_CHECK();
   }
-  k_tcw_scan<<<1, 1024, 0, s>>>(w.win_len, a.nr, w.win_rowptr);
-  FX_LAUNCH_CHECK();
+  FX_CUDA(device_exclusive_scan(a.spec_sort_tmp, a.spec_sort_tmp_bytes, w.win_len, a.nr, w.win_rowptr, s));
   k_tcw_scan<<<1, 1024, 0, s>>>(w.chunk_len, a.npanel * (w.W / 32), w.win_cptr);
   FX_LAUNCH_CHECK();
   k_tcw_rowptr<<<ceil_div(nloc + 1, 256), 256, 0, s>>>(w.csr_v, w.win_rowptr, nloc, w.rest_rowptr);
   FX_LAUNCH_CHECK();
   k_tcw_panels<<<1, 1024, 0, s>>>(w.tc_ncol, w.win_rowptr, a.npanel, a.nr, w.tc_panels, w.tc_slot, w.stats);
   FX_LAUNCH_CHECK();
-  const size_t split_smem = sizeof(int) * (size_t)(w.W / 32) * BH;
+  const size_t split_smem = sizeof(int) * (size_t)(w.W / 32) * BH + hash_bytes + sizeof(int) * (size_t)(w.W / 32) * 17;
   static SmemAttr split_attr;
   if (int rc = split_attr.ensure(k_tcw_split, split_smem)) return rc;
   k_tcw_split<<<a.G, 512, split_smem, s>>>(w.csr_v, col, val, w.win_rowptr, w.win_cptr, w.tc_cols, w.tc_ncol, a.npanel, (int)m->n,
