@@ -323,16 +323,25 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(
   }
   long long s1 = 0, s2 = 0;
   int chunks = 0;
-  for (int r = warp; r < BH; r += FILL_WARPS) {
+  if (tp == 0) {
+    // No dense tile in this panel: the nz keep their order.  One flat, coalesced copy by the whole CTA (a warp per row made
+    // the CTA wait for the warp that drew a hub row), then the per-row words.
+    const int lb = csr_v[p * BH], ub = csr_v[(p + 1) * BH];
+    for (int e = lb + threadIdx.x; e < ub; e += blockDim.x) { perm[e] = e; csr_e[e] = (int)col[e]; csr_ev[e] = val[e]; }
+    for (int r = threadIdx.x; r < BH; r += blockDim.x) {
+      const int row = p * BH + r;
+      const int rs = csr_v[row], len = csr_v[row + 1] - rs;
+      mcsr_e[cnt0 * BH + r] = rs;
+      spec_cnt[row] = len / STHRESHOLD;
+      s1 += len; s2 += (long long)len * len; chunks += len / STHRESHOLD;
+    }
+  }
+  for (int r = tp == 0 ? BH : warp; r < BH; r += FILL_WARPS) {
     const int row = p * BH + r;
     const int rs = csr_v[row], re = csr_v[row + 1];
     const int base = cnt0 * BH + r * delta;
     int len;
-    if (tp == 0) {
-      if (lane == 0) mcsr_e[base] = rs;
-      for (int e = rs + lane; e < re; e += 32) { perm[e] = e; csr_e[e] = (int)col[e]; csr_ev[e] = val[e]; }
-      len = re - rs;
-    } else {
+    {
       int* h = hist[warp];
       for (int g = lane; g < delta; g += 32) h[g] = 0;
       __syncwarp();
@@ -382,9 +391,15 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(
       s1 += len; s2 += (long long)len * len; chunks += len / STHRESHOLD;
     }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    chunks += __shfl_xor_sync(0xffffffffu, chunks, o);
+  }
   if (lane == 0) {
-    atomicAdd(&stats[0], (unsigned long long)s1);
-    atomicAdd(&stats[1], (unsigned long long)s2);
+    if (s1) atomicAdd(&stats[0], (unsigned long long)s1);
+    if (s2) atomicAdd(&stats[1], (unsigned long long)s2);
     if (chunks) atomicAdd(&stats[2], (unsigned long long)chunks);
   }
   if (p == npanel - 1 && threadIdx.x == 0) mcsr_e[(size_t)BH * mcsr_cnt[npanel]] = ne;  // :1297
