@@ -98,8 +98,7 @@ extern "C" int fx_comm_init(int nranks, int rank, const char id[128], fx_comm** 
             cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreate(&c->e0) == cudaSuccess && cudaEventCreate(&c->e1) == cudaSuccess;
   for (int i = 0; i < 8 && ok; ++i)
-    ok = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&c->ev_ag[i], cudaEventDisableTiming) == cudaSuccess &&
+    ok = cudaEventCreate(&c->ev_in[i]) == cudaSuccess && cudaEventCreate(&c->ev_ag[i]) == cudaSuccess &&
          cudaEventCreate(&c->ev_k[i]) == cudaSuccess && cudaEventCreate(&c->k0[i]) == cudaSuccess;
   if (!ok) { fx::set_error("fx_comm_init: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())); fx_comm_free(c); return FX_ERR_CUDA; }
   *out = c;
@@ -185,6 +184,19 @@ extern "C" int fx_spmm_sharded_host(const fx_tiles* t, fx_comm* c, const float* 
     float sum = 0.f, ms = 0.f;
     for (int i = 0; i < nchunk; ++i) { FX_CUDA(cudaEventElapsedTime(&ms, c->k0[i], c->ev_k[i])); sum += ms; }
     *tElap_ms = sum;
+  }
+  static const bool prof = getenv("FLEX_SHARD_PROF") != nullptr;  // time line of the call, ms after its start, per column chunk
+  if (prof) {
+    float tot = 0.f;
+    cudaEventElapsedTime(&tot, c->e0, c->e1);
+    fprintf(stderr, "[fx_spmm_sharded_host rank %d] total %.3f ms;", c->rank, tot);
+    for (int i = 0; i < nchunk; ++i) {
+      float a = 0.f, b = 0.f, k0 = 0.f, k1 = 0.f;
+      cudaEventElapsedTime(&a, c->e0, c->ev_in[i]); cudaEventElapsedTime(&b, c->e0, c->ev_ag[i]);
+      cudaEventElapsedTime(&k0, c->e0, c->k0[i]); cudaEventElapsedTime(&k1, c->e0, c->ev_k[i]);
+      fprintf(stderr, " chunk %d: slice in %.3f, all-gather done %.3f, SpMM %.3f-%.3f;", i, a, b, k0, k1);
+    }
+    fprintf(stderr, "\n");
   }
   return FX_OK;
 }
