@@ -38,6 +38,10 @@ def main():
     n, nnz = rp.numel() - 1, c.numel()
     rp32, c32 = rp.to(torch.int32), c.to(torch.int32)
     dl = fx.DataLoader.from_device(n, nnz, rp32.data_ptr(), c32.data_ptr(), v.data_ptr(), k, name + ".csv")
+    if os.environ.get("ORDER"):  # ORDER=deg|rcm|gor|rbt: the same sweep on the reordered matrix
+        import numpy as np
+        dl = fx.DataLoader.from_arrays(rp.cpu().numpy().astype(np.uint32), c.cpu().numpy().astype(np.uint32), v.cpu().numpy(), k, name + ".csv")
+        dl = dl.reorder({"deg": fx.FX_ORDER_DEG, "rcm": fx.FX_ORDER_RCM, "gor": fx.FX_ORDER_GOR, "rbt": fx.FX_ORDER_RBT}[os.environ["ORDER"]])
     B = synth.dense_B(n, k, device=dev)
     Cref = torch.empty((n, k), dtype=torch.float32, device=dev)
     Cd = torch.empty((n, k), dtype=torch.float32, device=dev)
