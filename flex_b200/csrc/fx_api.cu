@@ -122,6 +122,7 @@ extern "C" void fx_tiles_free(fx_tiles* t) {
   if (t->ev0) cudaEventDestroy(t->ev0);
   if (t->ev1) cudaEventDestroy(t->ev1);
   if (t->own_stream) cudaStreamDestroy(t->own_stream);
+  for (int i = 0; i < 64; ++i) if (t->pipe_g[i]) cudaEventDestroy(t->pipe_g[i]);
   for (int i = 0; i < 3; ++i) if (t->pipe_s[i]) cudaStreamDestroy(t->pipe_s[i]);
   for (int i = 0; i < 8; ++i) {
     if (t->pipe_in[i]) cudaEventDestroy(t->pipe_in[i]);
@@ -320,6 +321,13 @@ extern "C" int fx_spmm_host(const fx_tiles* tc, const float* B_host, float* C_ho
     const int cw = k / nchunk;
     const size_t pitch = sizeof(float) * (size_t)k, wbytes = sizeof(float) * (size_t)cw;
     const size_t nrowsB = (size_t)t->mat->n, nrowsC = (size_t)(t->row_end - t->row_begin);
+    // Row groups: a chunk's multiply is launched over NG ranges of 128-row panels, and the rows of a range are copied out as
+    // soon as that range is done -- the copy-out of chunk i starts one range (not one chunk) after its copy-in ended, so the
+    // D2H engine is free earlier for the last chunk, whose copy-out nothing overlaps.
+    static const int want_groups = getenv("FLEX_HOST_GROUPS") ? atoi(getenv("FLEX_HOST_GROUPS")) : 4;
+    const int npanel = t->aspt.npanel;
+    const int NG = std::max(1, std::min(std::min(want_groups, 8), npanel / 256));  // a range of fewer panels is under one wave
+    if (!t->pipe_g[0]) for (int i = 0; i < 64; ++i) FX_CUDA(cudaEventCreateWithFlags(&t->pipe_g[i], cudaEventDisableTiming));
     FX_CUDA(cudaEventRecord(t->pipe_e0, sin));
     for (int i = 0; i < nchunk; ++i) {
       const size_t c0 = (size_t)i * cw;
@@ -327,11 +335,18 @@ extern "C" int fx_spmm_host(const fx_tiles* tc, const float* B_host, float* C_ho
       FX_CUDA(cudaEventRecord(t->pipe_in[i], sin));
       FX_CUDA(cudaStreamWaitEvent(sk, t->pipe_in[i], 0));
       FX_CUDA(cudaEventRecord(t->pipe_k0[i], sk));
-      int rc = fx::spmm_aspt(t, t->B_stage_dev + c0, t->C_stage_dev + c0, k, sk, cw);
-      if (rc != FX_OK) return rc;
-      FX_CUDA(cudaEventRecord(t->pipe_k1[i], sk));
-      FX_CUDA(cudaStreamWaitEvent(sout, t->pipe_k1[i], 0));
-      if (nrowsC) FX_CUDA(cudaMemcpy2DAsync(C_host + c0, pitch, t->C_stage_dev + c0, pitch, wbytes, nrowsC, cudaMemcpyDeviceToHost, sout));
+      for (int g = 0; g < NG; ++g) {
+        const int p_lo = (int)((long long)npanel * g / NG), p_hi = (int)((long long)npanel * (g + 1) / NG);
+        int rc = fx::spmm_aspt(t, t->B_stage_dev + c0, t->C_stage_dev + c0, k, sk, cw, p_lo, p_hi);
+        if (rc != FX_OK) return rc;
+        cudaEvent_t done = g + 1 < NG ? t->pipe_g[i * 8 + g] : t->pipe_k1[i];
+        FX_CUDA(cudaEventRecord(done, sk));
+        FX_CUDA(cudaStreamWaitEvent(sout, done, 0));
+        const size_t r_lo = std::min(nrowsC, (size_t)p_lo * 128), r_hi = std::min(nrowsC, (size_t)p_hi * 128);
+        if (r_hi > r_lo)
+          FX_CUDA(cudaMemcpy2DAsync(C_host + r_lo * k + c0, pitch, t->C_stage_dev + r_lo * k + c0, pitch, wbytes, r_hi - r_lo,
+                                    cudaMemcpyDeviceToHost, sout));
+      }
     }
     FX_CUDA(cudaEventRecord(t->pipe_e1, sout));
     FX_CUDA(cudaEventSynchronize(t->pipe_e1));

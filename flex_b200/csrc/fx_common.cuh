@@ -211,6 +211,7 @@ struct fx_tiles {
   // fx_spmm_host pipeline: copy-in, compute and copy-out streams + per-chunk events (created on first use)
   cudaStream_t pipe_s[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t pipe_in[8] = {}, pipe_k0[8] = {}, pipe_k1[8] = {}, pipe_e0 = nullptr, pipe_e1 = nullptr;
+  cudaEvent_t pipe_g[64] = {};  // [chunk][row group]: "this range of panels is multiplied"
   // host copies for export
   std::vector<int32_t> h_chk, h_cnt, h_e, h_list, h_baddr, h_saddr, h_perm, h_csr_e, h_special, h_special2;
   std::vector<float> h_csr_ev;
@@ -235,7 +236,8 @@ void flex_release(fx_tiles* t);
 int spmm_csr(const uint32_t* rowptr, const uint32_t* col, const float* val, int64_t nrows, const float* B,
              float* C, int k, cudaStream_t s);
 // width > 0: compute only `width` feature columns starting at the B / C pointers (row stride stays k)
-int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s, int width = 0);
+// width: feature columns computed from the B/C pointers on (0 = k); [p_lo, p_hi): the 128-row panels multiplied (-1 = all)
+int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s, int width = 0, int p_lo = 0, int p_hi = -1);
 int spmm_aspt_times(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s, float ms[4]);
 int gemm_xw(const float* X, const float* W, float* out, int64_t rows, int k, int c, cudaStream_t s);
 int permute_rows(const int32_t* map, int64_t n, int k, const float* src, float* dst, bool scatter,

@@ -174,6 +174,7 @@ struct PanelArgs {
   int hints;            // L2 eviction priorities (make_policies)
   int team_row;         // rows of at least this many handled nz go to a team of four warps; 0 = by width (k_spmm_rows)
   int tiles_ok;         // bit 31 of a staged offset is free to flag "this B row is in the shared-memory tiles"
+  int p_lo, p_hi;       // only the panels in [p_lo, p_hi) are multiplied (row groups of the host pipeline, fx_spmm_host)
 };
 
 // ---- long-row chunks: partial[i,:] = sum over the i-th 512-nz chunk --------------------------
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special(PanelArgs a, 
   const int c4 = col_ok ? kc0 / 4 + sl : 0;
   const int row = special[item], off = special2[item];
   const int p = row / BH, r = row % BH;
+  if (p < a.p_lo || p >= a.p_hi) return;  // uniform over the tile
   const int cnt0 = a.mcsr_cnt[p], delta = a.mcsr_cnt[p + 1] - cnt0;
   // the row's nch chunks are its LAST nch*512 nz (the panel kernel streams everything before them)
   const int nch = a.spec_off[row + 1] - a.spec_off[row];
@@ -223,6 +225,7 @@ __global__ void __launch_bounds__(PANEL_WARPS * 32) k_spmm_special_cta(PanelArgs
   const int c4 = col_ok ? kc0 / 4 + sl : 0;
   const int row = special[item], off = special2[item];
   const int p = row / BH, r = row % BH;
+  if (p < a.p_lo || p >= a.p_hi) return;  // uniform over the CTA
   const int cnt0 = a.mcsr_cnt[p], delta = a.mcsr_cnt[p + 1] - cnt0;
   const int nch = a.spec_off[row + 1] - a.spec_off[row];
   const int lo = a.mcsr_e[cnt0 * BH + (r + 1) * delta] - nch * STHRESHOLD + off + wk * SLICE;
@@ -289,6 +292,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_spmm_rows(PanelArgs a, con
     part_q = blockIdx.x % a.split; split = a.split;
     p = plist ? plist[pslot] : pslot;
   }
+  if (p < a.p_lo || p >= a.p_hi) return;  // uniform over the CTA
   const int kc0 = blockIdx.y * KC;
   const int cnt0 = a.mcsr_cnt[p], delta = a.mcsr_cnt[p + 1] - cnt0;
   const int ntres = TILES ? min(delta - 1, a.TS) : 0;
@@ -690,15 +694,19 @@ static int launch_tc(const fxtc::TcArgs& ta, int ntc, cudaStream_t s) {
   return FX_OK;
 }
 
-int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s, int width) {
+int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s, int width, int p_lo, int p_hi) {
   if (width <= 0) width = k;
   const fx_aspt_dev& d = t->aspt;
   if (d.npanel == 0) return FX_OK;
+  if (p_hi < 0 || p_hi > d.npanel) p_hi = d.npanel;
+  if (p_lo < 0) p_lo = 0;
+  if (p_lo >= p_hi) return FX_OK;
   // float4 offsets of B rows are 32-bit in the kernels (both entry points, fx_spmm and fx_spmm_host, come through here)
   FX_REQUIRE((int64_t)t->mat->n * k / 4 < (1ll << 32), FX_ERR_UNSUPPORTED, "n*k too large for 32-bit float4 offsets");
   const int KC = pick_kc(width);
   PanelArgs a;
   a.tc_out = nullptr; a.tc_slot = nullptr; a.wl = nullptr;
+  a.p_lo = p_lo; a.p_hi = p_hi;
   static const int hints = getenv("FLEX_HINTS") ? atoi(getenv("FLEX_HINTS")) : 1;
   a.hints = hints;
   static const int team_row = getenv("FLEX_TEAM_ROW") ? atoi(getenv("FLEX_TEAM_ROW")) : 0;
@@ -712,6 +720,7 @@ int spmm_aspt(const fx_tiles* t, const float* B, float* C, int k, cudaStream_t s
     ta.tc_panels = w.tc_panels; ta.tc_cols = w.tc_cols; ta.tc_ncol = w.tc_ncol;
     ta.B = B; ta.out = w.tc_out; ta.k = k; ta.width = width; ta.W = w.W;
     ta.hints = getenv("FLEX_TC_HINTS") ? atoi(getenv("FLEX_TC_HINTS")) : hints;
+    ta.p_lo = p_lo; ta.p_hi = p_hi;
     const int rc = KC == 32 ? launch_tc<32>(ta, w.ntc, s) : (KC == 64 ? launch_tc<64>(ta, w.ntc, s) : launch_tc<128>(ta, w.ntc, s));
     if (rc != FX_OK) return rc;
     a.tc_out = w.tc_out; a.tc_slot = w.tc_slot;

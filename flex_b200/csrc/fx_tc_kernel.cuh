@@ -40,6 +40,7 @@ struct TcArgs {
   int k, W;   // k = row stride of B and out (floats)
   int width;  // feature columns computed, from the B/out pointers on
   int hints;  // L2 eviction priorities on (FLEX_HINTS)
+  int p_lo, p_hi;  // only the panels in [p_lo, p_hi) are multiplied (row groups of the host pipeline, fx_spmm_host)
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(256, 3) k_spmm_tc(TcArgs a) {
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slot = blockIdx.x, panel = a.tc_panels[slot], n0 = blockIdx.y * N;
+  if (panel < a.p_lo || panel >= a.p_hi) return;  // uniform over the CTA, before any allocation
   const int ncol = a.tc_ncol[panel];
   const int* cols = a.tc_cols + (size_t)panel * a.W;
 

@@ -227,7 +227,9 @@ int fx_spmm(const fx_tiles *t, const float *B_dev, float *C_dev, int k, void *st
  * ASpT / tensor-window handles only; waits for the step to finish. */
 int fx_spmm_kernel_times(const fx_tiles *t, const float *B_dev, float *C_dev, int k, void *stream, float ms[4]);
 /* Same with HOST buffers: copies B in, runs, copies C out (DataLoader.cu:216 + flex.cu:5690).
- * Uses an internal pinned staging area if the buffers are pageable. */
+ * ASpT / tensor-window handles with k % 32 == 0, k >= 64: pipelined over two column chunks (FLEX_HOST_CHUNKS) and, inside a
+ * chunk, over up to four ranges of row panels (FLEX_HOST_GROUPS) whose rows of C are copied out as soon as they are
+ * multiplied; tElap_ms is then the sum of the chunks' kernel sections.  Pass pinned buffers for full PCIe rate. */
 int fx_spmm_host(const fx_tiles *t, const float *B_host, float *C_host, int k, float *total_ms,
                  float *tElap_ms);
 
