@@ -3,7 +3,7 @@ yelp-shape k=128, yelp-shape + DEG / + Gorder, Amazon-shape k=128 -- each throug
 (reorder -> build -> gather B by vo_mp -> SpMM -> scatter C back) and checked IN THE ORIGINAL ORDER against the CPU oracle on
 sampled rows, plus the size-independent properties (checksum of checksums in fp64, run-to-run bit identity).
 
-The error report per configuration (gpurun_out/parity_report.jsonl, one line each; profiles/r2_parity.md is made from it):
+The error report per configuration (gpurun_out/parity_report.jsonl, one line each; profiles/r2_parity_report.jsonl is a copy of the last run):
   * the reference's validators: resCheck misses (flex.cu:4155) and the ASpT 1 % check (aspt/sspmm_128.cu:1425);
   * this repo's contract, row-normwise: |d| <= 1e-5 * max(1, ||gold[row,:]||_inf);
   * the ELEMENTWISE relative count the north star words literally (|d| > 1e-5 * |gold|, gold != 0) -- for the GPU result
