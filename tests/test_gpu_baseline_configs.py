@@ -10,7 +10,8 @@ The error report per configuration (gpurun_out/parity_report.jsonl, one line eac
     AND for the reference's own CPU loop, both against an fp64 accumulation of the same products: elementwise relative
     error is dominated by cancellation (|gold| << the row's scale), where two correct fp32 summation orders differ;
   * the principled bound asserted here: the GPU's error against fp64 is no larger than twice the error of the reference's
-    own fp32 CPU loop against fp64 (max and rms over the sampled elements).
+    own fp32 CPU loop against fp64 (max and rms over the sampled elements; rms within four times where 3xTF32 tensor windows
+    carry part of the nz -- see the comment at the assertion).
 """
 import json
 import os
@@ -31,6 +32,7 @@ CONFIGS = [
     ("yelp", 128, "ovo"),     # configs[3]
     ("yelp", 32, "deg"),      # configs[3]
     ("yelp", 128, "gor"),     # configs[3]
+    ("reddit", 128, "ovo"),   # configs[2], the headline: 41 % of the nz through the tcgen05 3xTF32 windows
     ("reddit", 128, "deg"),   # the hubs-first order that closes most windows
     ("amazon", 128, "ovo"),   # configs[4]
 ]
@@ -111,9 +113,13 @@ def test_baseline_config(orc, name, k, order):
     # off by up to 3e-3 where the GPU's blocked sum is off by 2e-4): misses there are the gold's, and are bounded by them.
     assert rep["rownorm_1e5_misses_gpu_vs_f64"] == 0, rep
     assert rep["rownorm_1e5_misses"] <= rep["rownorm_1e5_misses_cpu_vs_f64"], rep
-    # the GPU result is as close to the exact (fp64) product as the reference's own fp32 CPU loop, within a factor of two
+    # the GPU result is as close to the exact (fp64) product as the reference's own fp32 CPU loop, within a factor of two --
+    # for the all-FMA kernels.  Where nz go through the tensor windows the 3xTF32 split (hi.hi + hi.lo + lo.hi, lo.lo dropped,
+    # tensor-core accumulation) carries ~2^-22 per product against fp32's 2^-24: measured on Reddit-shape (41 % of the nz in
+    # windows) rms 4.9e-8 against the CPU loop's 1.6e-8, max 3.8e-7 against 1.0e-6 -- bounded here by four times the CPU
+    # loop's rms, and 25 times inside the 1e-5 contract asserted above.
     assert rep["max_abs_err_gpu_vs_f64"] <= 2.0 * rep["max_abs_err_cpu_vs_f64"] + 1e-7, rep
-    assert rep["rms_err_gpu_vs_f64"] <= 2.0 * rep["rms_err_cpu_vs_f64"] + 1e-9, rep
+    assert rep["rms_err_gpu_vs_f64"] <= (4.0 if info["win_nnz"] else 2.0) * rep["rms_err_cpu_vs_f64"] + 1e-9, rep
     # (2) run-to-run bit identity (no atomics anywhere on the path)
     C2 = torch.empty_like(C1)
     run(C2)
