@@ -89,7 +89,7 @@ class PillarArrays(C.Structure):
                 ("alpha_rowPtr", C.POINTER(C.c_uint32)), ("alpha_colIdx", C.POINTER(C.c_uint32)),
                 ("alpha_pillar_rowPtr", C.POINTER(C.c_uint32)), ("alpha_pillarIdx", C.POINTER(C.c_uint32)),
                 ("segVoMap", C.POINTER(C.c_uint32)), ("alpha_vals", C.POINTER(C.c_float)),
-                ("empty_wp_p", C.c_float), ("band_nz_p", C.c_float)]
+                ("empty_wp_p", C.c_float), ("band_nz_p", C.c_float), ("round1_on_gpu", C.c_int32)]
 
 
 class TcwArrays(C.Structure):
@@ -410,7 +410,7 @@ class Mat:
         a = PillarArrays()
         _ck(lib().fx_tiles_export_pillar(self._h, C.byref(a)))
         R, nnz = a.rows_total, a.nnz
-        return dict(n_segs=a.n_segs, rows_total=R, warps_with_weights=a.warps_with_weights, n_sm=a.n_sm,
+        return dict(n_segs=a.n_segs, rows_total=R, warps_with_weights=a.warps_with_weights, n_sm=a.n_sm, round1_on_gpu=a.round1_on_gpu,
                     empty_wp_p=a.empty_wp_p, band_nz_p=a.band_nz_p,
                     alpha_rowPtr=_np(a.alpha_rowPtr, R + 1, np.uint32).copy(),
                     alpha_colIdx=_np(a.alpha_colIdx, nnz, np.uint32).copy(),

@@ -32,6 +32,8 @@ struct fx_flex_dev {
   int* pstart = nullptr;                      // [partitions+1] first row of every diagonal block
   int *nzcnt = nullptr, *nzoff = nullptr;     // per row panel: nz left for round 3 and their exclusive scan
   int* perr = nullptr;                        // error flags of the device rounds
+  int *dpos = nullptr, *ends = nullptr;       // round 1 on the GPU: position of the diagonal in every row, end of the block starting at every row
+  bool round1_on_gpu = false;
   void* scan_tmp = nullptr;
   size_t scan_tmp_bytes = 0;
   int partitions = 0, r2_nnz = 0;

@@ -231,6 +231,73 @@ __global__ void __launch_bounds__(256) k_pillar_fill(PillarIn a, PillarOut o, in
   }
 }
 
+// Round 1 on the GPU, for the matrices every BASELINE shape is (diagonal stored in every row, structure symmetric near the
+// diagonal).  Round 1 (mat.cu:706-759) grows block i from its first row s until the nz inside the square [s, j) x [s, j) exceed
+// thr: with the diagonal present the walk of row j (mat.cu:718-727) counts the row's nz with s <= col <= j, and the column
+// sweep (mat.cu:729-743) counts the rows kk in [s, j) that hold column j -- by symmetry the row's nz with s <= col < j.  So the
+// end e(s) of a block depends on s alone and is computed for EVERY s in parallel (a thread per s, at most thr + 1 rows each:
+// every row adds at least its diagonal); the chain s -> e(s) over the 64 n_sm blocks is then followed on the host over one
+// downloaded array.  Anything else (a row without its diagonal, an nz within thr + 1 of the diagonal without its transpose)
+// goes to the host's round 1 (fx_flex_host.cu), which follows the reference statement by statement.
+__global__ void k_diag_pos(const unsigned* __restrict__ rowptr, const unsigned* __restrict__ col, int m, int* __restrict__ dpos,
+                           int* __restrict__ flags) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  unsigned lo = rowptr[r], hi = rowptr[r + 1];
+  while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (col[mid] < (unsigned)r) lo = mid + 1; else hi = mid; }
+  const bool ok = lo < rowptr[r + 1] && col[lo] == (unsigned)r;
+  dpos[r] = ok ? (int)lo : -1;
+  if (!ok) atomicExch(&flags[1], 1);
+}
+
+__device__ __forceinline__ bool row_has(const unsigned* __restrict__ rowptr, const unsigned* __restrict__ col, unsigned r, unsigned c) {
+  unsigned lo = rowptr[r], hi = rowptr[r + 1];
+  const unsigned end = hi;
+  while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (col[mid] < c) lo = mid + 1; else hi = mid; }
+  return lo < end && col[lo] == c;
+}
+
+// every nz (r, c) with 0 < |r - c| <= band has its transpose (only these can lie inside a diagonal square)
+__global__ void k_band_sym(const unsigned* __restrict__ rowptr, const unsigned* __restrict__ col, const int* __restrict__ dpos, int m,
+                           int band, int* __restrict__ flags) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m || dpos[r] < 0) return;
+  const int d = dpos[r];
+  for (int e = d - 1; e >= (int)rowptr[r] && (int)col[e] >= r - band; --e)
+    if (!row_has(rowptr, col, col[e], (unsigned)r)) { atomicExch(&flags[2], 1); return; }
+  for (int e = d + 1; e < (int)rowptr[r + 1] && (int)col[e] <= r + band; ++e)
+    if (!row_has(rowptr, col, col[e], (unsigned)r)) { atomicExch(&flags[2], 1); return; }
+}
+
+__global__ void k_diag_ends(const unsigned* __restrict__ rowptr, const unsigned* __restrict__ col, const int* __restrict__ dpos, int m,
+                            int thr, int* __restrict__ e_out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= m) return;
+  int cnt = 0, j = s;
+  while (j < m && cnt <= thr) {  // mat.cu:716
+    unsigned lo = rowptr[j], hi = (unsigned)dpos[j];
+    while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (col[mid] < (unsigned)s) lo = mid + 1; else hi = mid; }
+    const int a = dpos[j] - (int)lo + 1;  // nz of row j with s <= col <= j
+    cnt += 2 * a - 1;                     // + the rows of [s, j) that hold column j
+    ++j;
+  }
+  e_out[s] = j;
+}
+
+// listed[c] = 1 iff some nz (r, c) has r and c in the same diagonal block (mat.cu:722,737)
+__global__ void __launch_bounds__(256) k_diag_listed(const unsigned* __restrict__ rowptr, const unsigned* __restrict__ col,
+                                                     const int* __restrict__ pstart, int wpw, int m, unsigned char* __restrict__ listed) {
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (row >= m) return;
+  int lo = 0, hi = wpw;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pstart[mid] <= row) lo = mid; else hi = mid; }
+  const unsigned cs = (unsigned)pstart[lo], ce = (unsigned)pstart[lo + 1];
+  for (unsigned e = rowptr[row] + lane; e < rowptr[row + 1]; e += 32) {
+    const unsigned c = col[e];
+    if (c >= cs && c < ce) listed[c] = 1;
+  }
+}
+
 // csr2seg_Cmajor (mat.cu:1192-1269) over the nz round 2 left, nnz_limit = 128 (mat.cu:875 passes the member default)
 template <int TM, bool WRITE>
 __global__ void __launch_bounds__(128) k_pseg(PillarIn a, int npanels, int nnz_limit, int* __restrict__ segs_per_panel,
@@ -590,6 +657,7 @@ int flex_carve(fx_tiles* t) {
     const size_t rows_cap = (size_t)n + 1 + (size_t)f.seg_cap * f.tm + 2;
     add(sizeof(int) * (f.npanels + 2) * 2);   // nzcnt, nzoff
     add((size_t)n + 4); add(sizeof(int) * (f.partitions + 2));   // listed, pstart
+    add(sizeof(int) * (n + 2)); add(sizeof(int) * (n + 2));       // dpos, block ends (round 1 on the GPU)
     add(sizeof(int) * rows_cap); add(sizeof(int) * rows_cap);     // alpha_rowPtr, segVoMap
     add(sizeof(int) * (nnz + 2)); add(sizeof(float) * (nnz + 2)); // alpha_colIdx, alpha_vals
     add(sizeof(int) * ((size_t)f.partitions + f.seg_cap + 2));    // pillar_rowPtr
@@ -623,6 +691,7 @@ int flex_carve(fx_tiles* t) {
     const size_t rows_cap = (size_t)n + 1 + (size_t)f.seg_cap * f.tm + 2;
     f.nzcnt = A.take<int>(f.npanels + 2); f.nzoff = A.take<int>(f.npanels + 2);
     f.listed = A.take<unsigned char>(n + 4); f.pstart = A.take<int>(f.partitions + 2);
+    f.dpos = A.take<int>(n + 2); f.ends = A.take<int>(n + 2);
     f.alpha_rowPtr = A.take<unsigned>(rows_cap); f.segVoMap = A.take<unsigned>(rows_cap);
     f.alpha_colIdx = A.take<unsigned>(nnz + 2); f.alpha_vals = A.take<float>(nnz + 2);
     f.pillar_rowPtr = A.take<unsigned>((size_t)f.partitions + f.seg_cap + 2);
@@ -729,22 +798,59 @@ int flex_build(fx_tiles* t, cudaStream_t s) {
     std::vector<int> tile_width;
     std::vector<uint8_t> listed;
     int wpw = 0, rc = FX_OK;
-    // a matrix created from device arrays (fx_csr_from_device) has no host copy: its structure comes down once, inside tPre
-    std::vector<uint32_t> h_rowptr, h_col;
-    const uint32_t *hr = m->rowptr.data(), *hc = m->col.data();
-    if (m->col.empty() && f.nnz > 0) {
-      if ((rc = d2h(h_rowptr, m->rowptr_dev, (size_t)f.m + 1)) || (rc = d2h(h_col, m->col_dev, (size_t)f.nnz))) return rc;
-      hr = h_rowptr.data(); hc = h_col.data();
+    int* sh = reinterpret_cast<int*>(t->stats_host);
+    // round 1 on the GPU where its preconditions hold (see k_diag_ends), else on the host
+    const int nnz_p_diagonal_tile = std::max(32, (int)(0.3f * (float)m->rowptr[f.m]) / f.partitions);  // mat.cu:690-704
+    const int thr = (int)(0.85 * nnz_p_diagonal_tile);
+    static const int r1_env = getenv("FLEX_PILLAR_ROUND1") ? atoi(getenv("FLEX_PILLAR_ROUND1")) : -1;  // 0 = host, 1 = GPU if possible
+    bool on_gpu = false;
+    FX_CUDA(cudaMemsetAsync(f.perr, 0, sizeof(int) * 4, s));
+    if (r1_env != 0 && f.nnz > 0) {
+      k_diag_pos<<<ceil_div(f.m, 256), 256, 0, s>>>(m->rowptr_dev, m->col_dev, f.m, f.dpos, f.perr);
+      FX_LAUNCH_CHECK();
+      k_band_sym<<<ceil_div(f.m, 256), 256, 0, s>>>(m->rowptr_dev, m->col_dev, f.dpos, f.m, thr + 1, f.perr);
+      FX_LAUNCH_CHECK();
+      FX_CUDA(cudaMemcpyAsync(sh, f.perr, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+      FX_CUDA(cudaStreamSynchronize(s));
+      on_gpu = sh[1] == 0 && sh[2] == 0;
     }
-    rc = diag_round1_host(f.m, f.nnz, hr, hc, f.n_sm, tile_width, wpw, listed);
-    if (rc) return rc;
-    std::vector<int> pstart(wpw + 1, 0);
+    std::vector<int> pstart;
+    if (on_gpu) {
+      k_diag_ends<<<ceil_div(f.m, 128), 128, 0, s>>>(m->rowptr_dev, m->col_dev, f.dpos, f.m, thr, f.ends);
+      FX_LAUNCH_CHECK();
+      std::vector<int> ends((size_t)f.m);
+      FX_CUDA(cudaMemcpyAsync(ends.data(), f.ends, sizeof(int) * (size_t)f.m, cudaMemcpyDeviceToHost, s));
+      FX_CUDA(cudaStreamSynchronize(s));
+      tile_width.assign(f.partitions, 0);
+      int r0 = 0;
+      for (int i = 0; i < f.partitions && r0 < f.m; ++i) { tile_width[i] = ends[r0] - r0; r0 += tile_width[i]; ++wpw; }
+      FX_REQUIRE(r0 == f.m, FX_ERR_FORMAT, "alpha is too small: diagonal blocks cover %d of %d rows (assert mat.cu:759)", r0, f.m);
+      FX_REQUIRE(f.partitions != wpw, FX_ERR_FORMAT, "no idle warp left for the balance queue (division by zero at mat.cu:862)");
+    } else {
+      // a matrix created from device arrays (fx_csr_from_device) has no host copy: its structure comes down once, inside tPre
+      std::vector<uint32_t> h_rowptr, h_col;
+      const uint32_t *hr = m->rowptr.data(), *hc = m->col.data();
+      if (m->col.empty() && f.nnz > 0) {
+        if ((rc = d2h(h_rowptr, m->rowptr_dev, (size_t)f.m + 1)) || (rc = d2h(h_col, m->col_dev, (size_t)f.nnz))) return rc;
+        hr = h_rowptr.data(); hc = h_col.data();
+      }
+      rc = diag_round1_host(f.m, f.nnz, hr, hc, f.n_sm, tile_width, wpw, listed);
+      if (rc) return rc;
+    }
+    pstart.assign(wpw + 1, 0);
     for (int i = 0; i < wpw; ++i) pstart[i + 1] = pstart[i] + tile_width[i];
     FX_REQUIRE(pstart[wpw] == f.m, FX_ERR_FORMAT, "diagonal blocks do not cover every row (assert mat.cu:853)");
-    FX_CUDA(cudaMemcpyAsync(f.listed, listed.data(), (size_t)f.m, cudaMemcpyHostToDevice, s));
     FX_CUDA(cudaMemcpyAsync(f.pstart, pstart.data(), sizeof(int) * (wpw + 1), cudaMemcpyHostToDevice, s));
     FX_CUDA(cudaMemcpyAsync(f.pillar_rowPtr, pstart.data(), sizeof(int) * (wpw + 1), cudaMemcpyHostToDevice, s));
+    if (on_gpu) {
+      FX_CUDA(cudaMemsetAsync(f.listed, 0, (size_t)f.m, s));
+      k_diag_listed<<<ceil_div((long long)f.m * 32, 256), 256, 0, s>>>(m->rowptr_dev, m->col_dev, f.pstart, wpw, f.m, f.listed);
+      FX_LAUNCH_CHECK();
+    } else {
+      FX_CUDA(cudaMemcpyAsync(f.listed, listed.data(), (size_t)f.m, cudaMemcpyHostToDevice, s));
+    }
     FX_CUDA(cudaMemsetAsync(f.perr, 0, sizeof(int) * 4, s));
+    f.round1_on_gpu = on_gpu;
     PillarIn in{m->rowptr_dev, m->col_dev, m->val_dev, m->vo_mp_dev, f.listed, f.pstart, f.m, wpw};
     PillarOut o{f.alpha_rowPtr, f.alpha_colIdx, f.pillar_rowPtr, f.segVoMap, f.alpha_vals};
     // round 2 (mat.cu:771-835)
@@ -765,7 +871,6 @@ int flex_build(fx_tiles* t, cudaStream_t s) {
     switch (f.tm) { case 2: FX_PSEG(2, true); break; case 4: FX_PSEG(4, true); break; case 8: FX_PSEG(8, true); break; default: FX_PSEG(16, true); }
 #undef FX_PSEG
     FX_LAUNCH_CHECK();
-    int* sh = reinterpret_cast<int*>(t->stats_host);
     FX_CUDA(cudaMemcpyAsync(sh + 0, f.off + f.npanels, sizeof(int), cudaMemcpyDeviceToHost, s));
     FX_CUDA(cudaMemcpyAsync(sh + 1, f.count + (f.npanels - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
     FX_CUDA(cudaMemcpyAsync(sh + 2, f.alpha_rowPtr + f.m, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -902,5 +1007,6 @@ extern "C" int fx_tiles_export_pillar(fx_tiles* t, fx_pillar_arrays* o) {
   o->alpha_pillar_rowPtr = P.alpha_pillar_rowPtr.data(); o->alpha_pillarIdx = P.alpha_pillarIdx.data();
   o->segVoMap = P.segVoMap.data(); o->alpha_vals = P.alpha_vals.data();
   o->empty_wp_p = P.empty_wp_p; o->band_nz_p = P.band_nz_p;
+  o->round1_on_gpu = f.round1_on_gpu ? 1 : 0;
   return FX_OK;
 }

@@ -114,6 +114,8 @@ typedef struct { /* diagonal tiling / pillar format (mat.cu:680-903; Mat_POD mat
   const uint32_t *alpha_rowPtr, *alpha_colIdx, *alpha_pillar_rowPtr, *alpha_pillarIdx, *segVoMap;
   const float *alpha_vals;
   float empty_wp_p, band_nz_p;
+  int32_t round1_on_gpu; /* 1: the diagonal blocks (round 1) were grown on the GPU too; 0: on the host (a row without its
+                            diagonal, or an nz near the diagonal without its transpose) */
 } fx_pillar_arrays;
 
 typedef struct { /* tensor-window format (FX_FMT_TCW), host copies owned by the handle */

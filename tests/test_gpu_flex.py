@@ -76,6 +76,9 @@ def test_pillar_format(orc, data_dir, n_sm):
         for f in ("alpha_rowPtr", "alpha_colIdx", "alpha_vals", "alpha_pillar_rowPtr", "alpha_pillarIdx", "segVoMap"):
             assert np.array_equal(e[f], o[f]), (name, n_sm, f)
         assert e["n_segs"] == o["n_segs"] and abs(e["band_nz_p"] - o["band_nz_p"]) < 1e-5
+        # round 1 runs on the GPU for symmetric structures with a full diagonal, on the host otherwise (directed rnd900)
+        if name in ("sym1500", "rnd900"):
+            assert e["round1_on_gpu"] == (1 if name == "sym1500" else 0), (name, e["round1_on_gpu"])
         for k in (32, 128):
             B = rand_dense(dl.n, k, 3)
             gold = orc.spmm_ref(rp, c, v, B)
@@ -104,3 +107,27 @@ def test_reordered_seg_writes_original_order(orc, data_dir):
         torch.cuda.synchronize()
         assert_close(orc, orc.spmm_ref(rp, c, v, B), Cd.cpu().numpy(), rp)
         mat.free()
+
+
+@pytest.mark.parametrize("n,deg,seed", [(600, 3, 1), (3000, 12, 2), (5000, 40, 3), (2500, 80, 4)])
+@pytest.mark.parametrize("n_sm", [2, 8, 148])
+def test_pillar_round1_on_gpu(orc, n, deg, seed, n_sm):
+    """The GPU form of round 1 of csr2_DiagTiling (block end of every possible start in parallel, chain followed on the host)
+    against the reference-pinned oracle: symmetric graphs of several densities, few and many diagonal blocks."""
+    rp, c, v = small_graph(n, deg, seed, True)
+    dl = fx.DataLoader.from_arrays(rp, c, v, 32, f"sym{n}.csv")
+    try:
+        o = orc.diag_tiling(rp, c, v, dl.vo_mp, 4, n_sm)
+    except ValueError:
+        with pytest.raises(fx.FlexError):
+            fx.Mat(dl, fmt="pillar", tm=4, n_sm=n_sm)
+        return
+    mat = fx.Mat(dl, fmt="pillar", tm=4, n_sm=n_sm)
+    e = mat.export_pillar()
+    assert e["round1_on_gpu"] == 1
+    for f in ("alpha_rowPtr", "alpha_colIdx", "alpha_vals", "alpha_pillar_rowPtr", "alpha_pillarIdx", "segVoMap"):
+        assert np.array_equal(e[f], o[f]), (n, deg, n_sm, f)
+    assert e["warps_with_weights"] == o["warps_with_weights"] if "warps_with_weights" in o else True
+    B = rand_dense(n, 32, 5)
+    assert_close(orc, orc.spmm_ref(rp, c, v, B), run_spmm(mat, B, n), rp)
+    mat.free()
