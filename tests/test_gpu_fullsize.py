@@ -176,3 +176,32 @@ def test_flex_formats_full_size(orc, name, k, fmt, order):
         np.logical_or.at(flagged, vo, (p["segVoMap"] >> 31).astype(bool))
         assert np.array_equal(multi, flagged)
     mat.free()
+
+
+@pytest.mark.parametrize("name,k", [("flickr", 128), ("reddit", 128), ("reddit", 64)])  # 2 / 4 / 4 row groups (shards: 1 / 2 / 2)
+def test_host_path_row_groups_full_size(name, k):
+    """fx_spmm_host at full size: two column chunks x row groups (panel-range launches of the three kernels, copy-out per
+    range).  Every row belongs to exactly one group, so the result must equal the device-buffer SpMM of the same handle on
+    the same column chunking -- compared here with fx_spmm on each 64-column half (bit for bit) -- also for a row shard."""
+    import torch
+    rp, c, v = synth.generate(name, device="cuda")
+    n, nnz = rp.numel() - 1, c.numel()
+    rp32, c32 = rp.to(torch.int32), c.to(torch.int32)
+    dl = fx.DataLoader.from_device(n, nnz, rp32.data_ptr(), c32.data_ptr(), v.data_ptr(), k, name + ".csv")
+    B = synth.dense_B(n, k, device="cuda")
+    Bh = B.cpu().numpy()
+    rph = rp.cpu().numpy()
+    for lo, hi in ((0, n), ((n // 3) // 128 * 128, (2 * n // 3) // 128 * 128)):
+        mat = fx.Mat(dl, fmt="tcw", row_begin=lo, row_end=hi) if (lo, hi) != (0, n) else fx.Mat(dl, fmt="tcw")
+        out = np.full((hi - lo, k), np.nan, np.float32)
+        mat.spmm_host(Bh, out=out)
+        assert np.isfinite(out).all()
+        # the device path on the same column chunks: a [n x cw] copy of each half of B, SpMM with k = cw
+        cw = k // 2
+        for h in range(2):
+            Bc = B[:, h * cw:(h + 1) * cw].contiguous()
+            Cc = torch.empty((hi - lo, cw), device="cuda")
+            mat.spmm(Bc.data_ptr(), Cc.data_ptr(), cw)
+            torch.cuda.synchronize()
+            assert np.array_equal(out[:, h * cw:(h + 1) * cw], Cc.cpu().numpy()), (name, k, lo, hi, h)
+        mat.free()
