@@ -483,8 +483,6 @@ __global__ void __launch_bounds__(256) k_spmm_panel_acc(AccArgs a) {
   if (MODE == 0) { lo = a.tileNnz[a.tileRowPtr[p]]; hi = a.tileNnz[a.tileRowPtr[p + 1]]; }
   else { lo = a.segPtr[a.seg_off[p]]; hi = a.segPtr[a.seg_off[p + 1]]; }
   unsigned tcur = MODE == 0 ? a.tileRowPtr[p] : 0;
-  unsigned last_col = NOCOL;
-  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
   for (unsigned e0 = lo; e0 < hi; e0 += LPR) {
     const unsigned e = e0 + sl;
     int r = 0; unsigned c = 0; float v = 0.f;
@@ -506,14 +504,28 @@ __global__ void __launch_bounds__(256) k_spmm_panel_acc(AccArgs a) {
       while (a.tileNnz[tcur + 1] <= elast) ++tcur;
     }
     const int cnt = (int)min((unsigned)LPR, hi - e0);
-    for (int j = 0; j < cnt; ++j) {
-      const unsigned cc = tile.shfl(c, j);
-      const int rr = tile.shfl(r, j);
-      const float vv = tile.shfl(v, j);
-      if (cc != last_col) { b = __ldg(B4 + (size_t)cc * k4); last_col = cc; }  // column-major order: reuse the B row
-      float4 x = acc[rr * LPR];
-      x.x = fmaf(vv, b.x, x.x); x.y = fmaf(vv, b.y, x.y); x.z = fmaf(vv, b.z, x.z); x.w = fmaf(vv, b.w, x.w);
-      acc[rr * LPR] = x;
+    // the B rows of GB nz are requested before their FMAs (one load in flight per worker left this kernel waiting on L2:
+    // 68 stalled warps per issue); a column repeated by the next nz of the stream is an L1 hit
+    constexpr int GB = LPR < 8 ? LPR : 8;
+    for (int j0 = 0; j0 < cnt; j0 += GB) {
+      float4 bb[GB];
+      int rr[GB];
+      float vv[GB];
+#pragma unroll
+      for (int u = 0; u < GB; ++u) {
+        const int j = (j0 + u) & (LPR - 1);
+        const unsigned cc = tile.shfl(c, j);
+        rr[u] = tile.shfl(r, j);
+        vv[u] = tile.shfl(v, j);
+        bb[u] = j0 + u < cnt ? __ldg(B4 + (size_t)cc * k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < GB; ++u)
+        if (j0 + u < cnt) {
+          float4 x = acc[rr[u] * LPR];
+          x.x = fmaf(vv[u], bb[u].x, x.x); x.y = fmaf(vv[u], bb[u].y, x.y); x.z = fmaf(vv[u], bb[u].z, x.z); x.w = fmaf(vv[u], bb[u].w, x.w);
+          acc[rr[u] * LPR] = x;
+        }
     }
   }
   if (col_ok)
@@ -556,8 +568,31 @@ __global__ void __launch_bounds__(256) k_spmm_alpha(AlphaArgs a) {
   // flex.cu:4010), then it sweeps every other SM's queue.  The sweep is what makes the result independent of CTA
   // placement: the reference relies on a CTA landing on every SM, which CUDA does not promise (a second feature chunk,
   // opts.n_sm above the SM count, or another kernel on the GPU left queues undrained and rows of C silently zero).
-  for (int phase = 0; phase < 2 + a.n_sm; ++phase) {
-    const int q = phase == 0 ? q_own : (phase == 1 ? a.n_sm : (q_own + phase - 1) % a.n_sm);
+  // (The sweep looks at 32 queues per step -- a lane per queue reads its counter from L2 -- and visits only those with
+  // unclaimed pillars: walking all n_sm queues one by one cost every warp ~150 dependent round trips, 0.3 of the 0.5 ms
+  // of this kernel on flickr-shape.)
+  unsigned sweep_mask = 0;
+  int sweep_next = 0, sweep_base = 0;
+  for (int phase = 0;; ++phase) {
+    int q;
+    if (phase == 0) q = q_own;
+    else if (phase == 1) q = a.n_sm;
+    else {
+      while (sweep_mask == 0u && sweep_next < a.n_sm) {
+        const int cand = sweep_next + lane;
+        bool rem = false;
+        if (cand < a.n_sm && cand != q_own) {
+          const unsigned size = a.pillarIdx[cand + 1] - a.pillarIdx[cand];
+          rem = __ldcg(&a.counter[cand * gridDim.y + blockIdx.y]) < size;
+        }
+        sweep_mask = __ballot_sync(0xffffffffu, rem);
+        sweep_base = sweep_next;
+        sweep_next += 32;
+      }
+      if (sweep_mask == 0u) break;
+      q = sweep_base + (__ffs(sweep_mask) - 1);
+      sweep_mask &= sweep_mask - 1u;
+    }
     const unsigned qbeg = a.pillarIdx[q], qend = a.pillarIdx[q + 1];
     if (qbeg == qend) continue;
     while (true) {
@@ -566,25 +601,48 @@ __global__ void __launch_bounds__(256) k_spmm_alpha(AlphaArgs a) {
       pil = __shfl_sync(0xffffffffu, pil, 0);
       if (pil >= qend) break;
       const unsigned r0 = a.pillar_rowPtr[pil], r1 = a.pillar_rowPtr[pil + 1];
+      // the row pointers and output maps of up to 32 rows of the pillar in one coalesced load each (they were two dependent
+      // loads per row in front of the row's nz)
+      unsigned rp_l = 0, vm_l = 0, rbase = r0;
       for (unsigned rb = r0; rb < r1; rb += RPW) {
+        if (rb == r0 || rb + RPW > rbase + 31) {
+          rbase = rb;
+          rp_l = rbase + lane <= r1 ? a.alpha_rowPtr[rbase + lane] : 0u;
+          vm_l = rbase + lane < r1 ? a.segVoMap[rbase + lane] : 0u;
+        }
         const unsigned r = rb + sub;
         const bool act = r < r1;
-        const unsigned lo = act ? a.alpha_rowPtr[r] : 0, hi = act ? a.alpha_rowPtr[r + 1] : 0;
+        const int li = (int)(r - rbase);  // <= 31 - 1: the entry after the row's is in the same load (or the row is inactive)
+        const unsigned lo_s = __shfl_sync(0xffffffffu, rp_l, li & 31), hi_s = __shfl_sync(0xffffffffu, rp_l, (li + 1) & 31);
+        const unsigned vm_s = __shfl_sync(0xffffffffu, vm_l, li & 31);
+        const unsigned lo = act ? lo_s : 0, hi = act ? hi_s : 0;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (unsigned e0 = lo; e0 < hi; e0 += LPR) {
           const unsigned e = e0 + sl;
           unsigned off = 0; float v = 0.f;
           if (e < hi) { off = a.alpha_colIdx[e] * k4; v = a.alpha_vals[e]; }
           const int cnt = (int)min((unsigned)LPR, hi - e0);
-          for (int j = 0; j < cnt; ++j) {
-            const unsigned o = tile.shfl(off, j);
-            const float vv = tile.shfl(v, j);
-            const float4 b = __ldg(B4 + o);
-            acc.x = fmaf(vv, b.x, acc.x); acc.y = fmaf(vv, b.y, acc.y); acc.z = fmaf(vv, b.z, acc.z); acc.w = fmaf(vv, b.w, acc.w);
+          constexpr int GB = LPR < 8 ? LPR : 8;  // B rows requested before their FMAs
+          for (int j0 = 0; j0 < cnt; j0 += GB) {
+            float4 bb[GB];
+            float vv[GB];
+#pragma unroll
+            for (int u = 0; u < GB; ++u) {
+              const int j = (j0 + u) & (LPR - 1);
+              const unsigned o = tile.shfl(off, j);
+              vv[u] = tile.shfl(v, j);
+              bb[u] = j0 + u < cnt ? __ldg(B4 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < GB; ++u)
+              if (j0 + u < cnt) {
+                acc.x = fmaf(vv[u], bb[u].x, acc.x); acc.y = fmaf(vv[u], bb[u].y, acc.y);
+                acc.z = fmaf(vv[u], bb[u].z, acc.z); acc.w = fmaf(vv[u], bb[u].w, acc.w);
+              }
           }
         }
         if (act && col_ok) {
-          const unsigned vm = a.segVoMap[r];
+          const unsigned vm = vm_s;
           float* dst = a.C + (size_t)(vm & 0x7fffffffu) * a.k + (size_t)c4 * 4;
           if (vm & 0x80000000u) {  // the row has nz in other pillars too: accumulate (flex.cu:4108-4118)
             if (hi > lo) { atomicAdd(dst, acc.x); atomicAdd(dst + 1, acc.y); atomicAdd(dst + 2, acc.z); atomicAdd(dst + 3, acc.w); }
