@@ -32,6 +32,8 @@ struct fx_flex_dev {
   int* pstart = nullptr;                      // [partitions+1] first row of every diagonal block
   int *nzcnt = nullptr, *nzoff = nullptr;     // per row panel: nz left for round 3 and their exclusive scan
   int* perr = nullptr;                        // error flags of the device rounds
+  unsigned* rest_col = nullptr;               // the nz round 2 leaves, compacted row by row (input of round 3)
+  float* rest_val = nullptr;
   int *dpos = nullptr, *ends = nullptr;       // round 1 on the GPU: position of the diagonal in every row, end of the block starting at every row
   bool round1_on_gpu = false;
   void* scan_tmp = nullptr;

@@ -61,20 +61,29 @@ __global__ void __launch_bounds__(128) k_seg(const unsigned* __restrict__ rowptr
   int emitted = 0, nnzInSeg = 0, nseg = 0, atom = 0;
   int remaining = (int)(rowptr[rowEnd] - panel_base);
   const int s0 = WRITE ? seg_off[p] : 0;
+  // the lane's current (column, value) and the pair after it: the next pair is requested when the current one is taken.
+  // (tried: the lane's next 32 columns in shared memory, refilled 32 loads at a time, and a bulk step when a single row is
+  // left -- both slower: a step of the sweep is a ~350-clk chain of dependent shuffles and votes, not a wait for a load, and
+  // the rows of a panel all reach to the last columns, so a hub row is never "alone".  The sweep of the panel that holds the
+  // longest row IS the kernel's duration: 18 k steps on Reddit-shape.)
+  unsigned c = cur < re ? col[cur] : NOCOL, cn = cur + 1 < re ? col[cur + 1] : NOCOL;
+  float v = (WRITE && cur < re) ? val[cur] : 0.f, vn = (WRITE && cur + 1 < re) ? val[cur + 1] : 0.f;
   while (remaining > 0 || nnzInSeg > 0) {
     if (remaining > 0) {
-      const unsigned c = cur < re ? col[cur] : NOCOL;
       const unsigned j = cg::reduce(tile, c, cg::less<unsigned>());
-      const bool take = c == j;
+      const bool take = c == j;  // a lane without nz holds NOCOL, never the minimum while nz remain
       const unsigned bal = tile.ballot(take);
       if (take) {
         if (WRITE) {  // C-major stream: position in consumption order
           const unsigned pos = panel_base + emitted + nnzInSeg + __popc(bal & ((1u << lane) - 1u));
           o.segNzRCIdx[2 * (size_t)pos] = lane;
           o.segNzRCIdx[2 * (size_t)pos + 1] = c;
-          o.segVals[pos] = val[cur];
+          o.segVals[pos] = v;
         }
         ++cur; ++atom;
+        c = cn; v = vn;
+        cn = cur + 1 < re ? col[cur + 1] : NOCOL;
+        if (WRITE) vn = cur + 1 < re ? val[cur + 1] : 0.f;
       }
       const int took = __popc(bal);
       nnzInSeg += took; remaining -= took;
@@ -170,6 +179,8 @@ struct PillarIn {
 struct PillarOut {
   unsigned *alpha_rowPtr, *alpha_colIdx, *pillar_rowPtr, *segVoMap;
   float* alpha_vals;
+  unsigned* rest_col;  // the nz round 2 did not take, row by row: row r at [rowptr[r] - alpha_rowPtr[r], rowptr[r+1] - alpha_rowPtr[r+1])
+  float* rest_val;
 };
 
 // column window of the SM that owns `row` (mat.cu:773-779): the rows of the group of 64 blocks holding the row's block
@@ -215,19 +226,24 @@ __global__ void __launch_bounds__(256) k_pillar_fill(PillarIn a, PillarOut o, in
   unsigned cs, ce;
   sm_window(a, row, cs, ce);
   const unsigned rs = a.rowptr[row], re = a.rowptr[row + 1];
-  unsigned base = o.alpha_rowPtr[row];
+  unsigned base = o.alpha_rowPtr[row], rbase = rs - base;
   for (unsigned e0 = rs; e0 < re; e0 += 32) {
     const unsigned e = e0 + lane;
     unsigned c = 0;
     bool t = false;
     if (e < re) { c = a.col[e]; t = r2_takes(a, c, cs, ce); }
-    const unsigned bal = __ballot_sync(0xffffffffu, t);
+    const unsigned bal = __ballot_sync(0xffffffffu, t), balr = __ballot_sync(0xffffffffu, e < re && !t);
     if (t) {
       const unsigned pos = base + __popc(bal & ((1u << lane) - 1u));
       o.alpha_colIdx[pos] = c;
       o.alpha_vals[pos] = a.val[e];
+    } else if (e < re) {  // left for round 3: compacted, so that its sweep reads a plain CSR
+      const unsigned pos = rbase + __popc(balr & ((1u << lane) - 1u));
+      o.rest_col[pos] = c;
+      o.rest_val[pos] = a.val[e];
     }
     base += __popc(bal);
+    rbase += __popc(balr);
   }
 }
 
@@ -311,14 +327,21 @@ __global__ void __launch_bounds__(128) k_pseg(PillarIn a, int npanels, int nnz_l
   const int dif = (int)(0.1 * nnz_limit);
   const bool has_row = lane < rows;
   const int row = rowStart + lane;
-  const unsigned rs = has_row ? a.rowptr[row] : 0, re = has_row ? a.rowptr[row + 1] : 0;
-  unsigned cs = 0, ce = 0;
-  if (has_row) sm_window(a, row, cs, ce);
-  auto skip = [&](unsigned e) {
-    while (e < re && r2_takes(a, a.col[e], cs, ce)) ++e;
-    return e;
-  };
-  unsigned cur = skip(rs), prev = cur;
+  // the row's remainder after round 2, compacted by k_pillar_fill; `full` = the whole row's length (MSB rule, mat.cu:1252)
+  unsigned rs = 0, re = 0;
+  int full = 0;
+  if (has_row) {
+    const unsigned g0 = a.rowptr[row], g1 = a.rowptr[row + 1];
+    rs = g0 - o.alpha_rowPtr[row];
+    re = g1 - o.alpha_rowPtr[row + 1];
+    full = (int)(g1 - g0);
+  }
+  const unsigned* __restrict__ rcol = o.rest_col;
+  const float* __restrict__ rval = o.rest_val;
+  unsigned cur = rs, prev = rs;
+  // the lane's current column and the one after it (see k_seg)
+  unsigned c = cur < re ? rcol[cur] : NOCOL;
+  unsigned cn = cur + 1 < re ? rcol[cur + 1] : NOCOL;
   int emitted = 0, nnzInSeg = 0, nseg = 0, atom = 0;
   const unsigned r2 = WRITE ? o.alpha_rowPtr[a.m] : 0;
   const int s0 = WRITE ? seg_off[p] : 0;
@@ -326,10 +349,13 @@ __global__ void __launch_bounds__(128) k_pseg(PillarIn a, int npanels, int nnz_l
   bool left = tile.any(cur < re);
   while (left || nnzInSeg > 0) {
     if (left) {
-      const unsigned c = cur < re ? a.col[cur] : NOCOL;
       const unsigned j = cg::reduce(tile, c, cg::less<unsigned>());
-      const bool take = c == j;
-      if (take) { cur = skip(cur + 1); ++atom; }
+      const bool take = c == j;  // a lane without nz holds NOCOL, which is never the minimum while any nz is left
+      if (take) {
+        ++cur; ++atom;
+        c = cn;
+        cn = cur + 1 < re ? rcol[cur + 1] : NOCOL;
+      }
       nnzInSeg += __popc(tile.ballot(take));
       left = tile.any(cur < re);
     }
@@ -341,15 +367,12 @@ __global__ void __launch_bounds__(128) k_pseg(PillarIn a, int npanels, int nnz_l
         if (has_row) {
           o.alpha_rowPtr[a.m + 1 + rbase + lane] = seg_base + ex + atom;  // end of the virtual row; its start is the entry before
           unsigned w = seg_base + ex;
-          for (unsigned e = prev; e < cur; ++e) {
-            const unsigned cc = a.col[e];
-            if (r2_takes(a, cc, cs, ce)) continue;
-            o.alpha_colIdx[w] = cc;
-            o.alpha_vals[w] = a.val[e];
-            ++w;
+          for (unsigned e = prev; e < cur; ++e, ++w) {
+            o.alpha_colIdx[w] = rcol[e];
+            o.alpha_vals[w] = rval[e];
           }
           const unsigned v = (unsigned)a.vo_mp[row];
-          o.segVoMap[a.m + rbase + lane] = atom < (int)(re - rs) ? (v | 0x80000000u) : v;  // mat.cu:1252-1260
+          o.segVoMap[a.m + rbase + lane] = atom < full ? (v | 0x80000000u) : v;  // mat.cu:1252-1260
         }
         if (lane == 0) o.pillar_rowPtr[a.wpw + s0 + nseg] = (unsigned)(a.m + rbase);
       }
@@ -718,6 +741,7 @@ int flex_carve(fx_tiles* t) {
     add(sizeof(int) * (n + 2)); add(sizeof(int) * (n + 2));       // dpos, block ends (round 1 on the GPU)
     add(sizeof(int) * rows_cap); add(sizeof(int) * rows_cap);     // alpha_rowPtr, segVoMap
     add(sizeof(int) * (nnz + 2)); add(sizeof(float) * (nnz + 2)); // alpha_colIdx, alpha_vals
+    add(sizeof(int) * (nnz + 2)); add(sizeof(float) * (nnz + 2)); // rest_col, rest_val (what round 2 leaves for round 3)
     add(sizeof(int) * ((size_t)f.partitions + f.seg_cap + 2));    // pillar_rowPtr
     add(sizeof(int) * (f.n_sm + 2)); add(sizeof(int) * (f.n_sm + 1) * 16); add(sizeof(int) * 4);  // pillarIdx, counter, perr
     f.scan_tmp_bytes = 0;
@@ -752,6 +776,7 @@ int flex_carve(fx_tiles* t) {
     f.dpos = A.take<int>(n + 2); f.ends = A.take<int>(n + 2);
     f.alpha_rowPtr = A.take<unsigned>(rows_cap); f.segVoMap = A.take<unsigned>(rows_cap);
     f.alpha_colIdx = A.take<unsigned>(nnz + 2); f.alpha_vals = A.take<float>(nnz + 2);
+    f.rest_col = A.take<unsigned>(nnz + 2); f.rest_val = A.take<float>(nnz + 2);
     f.pillar_rowPtr = A.take<unsigned>((size_t)f.partitions + f.seg_cap + 2);
     f.pillarIdx = A.take<unsigned>(f.n_sm + 2); f.counter = A.take<unsigned>((f.n_sm + 1) * 16); f.perr = A.take<int>(4);
     f.scan_tmp = A.take<char>(f.scan_tmp_bytes);
@@ -910,7 +935,7 @@ int flex_build(fx_tiles* t, cudaStream_t s) {
     FX_CUDA(cudaMemsetAsync(f.perr, 0, sizeof(int) * 4, s));
     f.round1_on_gpu = on_gpu;
     PillarIn in{m->rowptr_dev, m->col_dev, m->val_dev, m->vo_mp_dev, f.listed, f.pstart, f.m, wpw};
-    PillarOut o{f.alpha_rowPtr, f.alpha_colIdx, f.pillar_rowPtr, f.segVoMap, f.alpha_vals};
+    PillarOut o{f.alpha_rowPtr, f.alpha_colIdx, f.pillar_rowPtr, f.segVoMap, f.alpha_vals, f.rest_col, f.rest_val};
     // round 2 (mat.cu:771-835)
     const int rgrid = ceil_div(((long long)f.m + 1) * 32, 256);
     k_pillar_count<<<rgrid, 256, 0, s>>>(in, o);

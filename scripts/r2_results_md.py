@@ -38,7 +38,7 @@ out += ["", "Notes.",
         "- Flex formats (K2 consumers) at k=128, pillar / seg / tile: pubmed 259 / 782 / 515 GFLOP/s (the reference's own v36 kernel on the same box: 45-53), flickr-shape 1 714 / 828 / 493",
         "  (v36: 230-334; `r2_ref_flex_v36_context.log`). Round-2 changes to these kernels: the B rows of 8 nz requested before their FMAs (seg 0.56 -> 0.30 ms, tile 0.80 -> 0.51 on",
         "  flickr-shape) and, in the pillar kernel, the sweep over the other SMs' queues looks at 32 queues per step instead of visiting all 148 one by one (0.52 -> 0.145 ms).",
-        "- Builds of the Flex formats (`scripts/r2_flex_tpre.py`, rebuilds): flickr-shape pillar 2.0 ms (49.3 all on the host -> 13.2 with rounds 2-3 on the GPU -> 2.0 with round 1 there too), seg 1.19, tile 1.50;",
-        "  Reddit-shape pillar 19.0 ms (169 with round 1 on the host), seg 12.2, tile 12.3; ASpT 0.09 / 1.61 ms, tensor windows 0.28 / 1.93 ms (flickr- / Reddit-shape)."]
+        "- Builds of the Flex formats (`scripts/r2_flex_tpre.py`, rebuilds): flickr-shape pillar 1.5 ms (49.3 all on the host -> 13.2 with rounds 2-3 on the GPU -> 2.0 with round 1 there too -> 1.5 sweeping a compacted remainder), seg 1.19, tile 1.50;",
+        "  Reddit-shape pillar 13.8 ms (169 with round 1 on the host), seg 12.2, tile 12.3; ASpT 0.09 / 1.61 ms, tensor windows 0.28 / 1.93 ms (flickr- / Reddit-shape)."]
 open(os.path.join(ROOT, "profiles", "r2_results.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out[-16:]))
