@@ -40,7 +40,7 @@ __global__ void k_pad_rowptr(const uint32_t* __restrict__ rowptr, int row0, int 
 }
 
 // ---- K1: dense_block_detect (:831-868) ----------------------------------------------------
-__global__ void __launch_bounds__(256) k_detect(const int* __restrict__ csr_v, const uint32_t* __restrict__ col,
+__global__ void __launch_bounds__(1024) k_detect(const int* __restrict__ csr_v, const uint32_t* __restrict__ col,
                                                 int min_occ, int* __restrict__ chk,
                                                 unsigned long long* __restrict__ stats) {
   __shared__ int hist[SC_SIZE];
@@ -91,7 +91,7 @@ __device__ void block_sort_u64(unsigned long long* a, int n) {
   }
 }
 
-__global__ void __launch_bounds__(512) k_heavy(const int* __restrict__ csr_v, const uint32_t* __restrict__ col,
+__global__ void __launch_bounds__(1024) k_heavy(const int* __restrict__ csr_v, const uint32_t* __restrict__ col,
                                                const int* __restrict__ chk, int npanel, int BW, int min_occ,
                                                int ncols, unsigned* __restrict__ cnt_all,
                                                unsigned long long* __restrict__ heavy_all, int* __restrict__ nheavy,
@@ -475,10 +475,9 @@ static int sm_count() {
 
 static int heavy_ctas(int npanel) {
   const int sm = sm_count();
-  int g = 2 * sm;  // 3 per SM measured no better (tPre 3.89 vs 4.07 ms TCW, 1.83 vs 1.73 ms ASpT on Reddit-shape)
-  // FLEX_BUILD_CTAS: persistent CTAs of the counting kernels.  Every CTA owns one counter per column (4 B x ncols), so the
-  // default is 276 MB of counters on Reddit-shape -- more than L2; fewer CTAs trade parallelism for L2-resident counters
-  // (unmeasured: added after the round's GPU budget was spent)
+  int g = build_threads() > 512 ? sm : 2 * sm;  // one 1024-thread CTA per SM (fx_common.cuh:build_threads), or two of 512
+  // FLEX_BUILD_CTAS: persistent CTAs of the counting kernels.  Every CTA owns one counter per column (4 B x ncols): 138 MB on
+  // Reddit-shape with one CTA per SM (276 MB with two, as in round 1)
   static const int g_env = getenv("FLEX_BUILD_CTAS") ? atoi(getenv("FLEX_BUILD_CTAS")) : 0;
   if (g_env > 0) g = g_env;
   return npanel < g ? (npanel > 0 ? npanel : 1) : g;
@@ -569,7 +568,7 @@ int aspt_build(fx_tiles* t, cudaStream_t s) {
   FX_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(unsigned long long) * 16, s));
   k_pad_rowptr<<<ceil_div(a.nr + 1, 256), 256, 0, s>>>(src_rowptr, src_row0, nloc, a.nr, a.ne, a.csr_v);
   FX_LAUNCH_CHECK();
-  k_detect<<<a.npanel, 256, 0, s>>>(a.csr_v, col, min_occ, a.mcsr_chk, a.stats);
+  k_detect<<<a.npanel, build_threads(), 0, s>>>(a.csr_v, col, min_occ, a.mcsr_chk, a.stats);
   FX_LAUNCH_CHECK();
   // the one decision the host has to take (reference: d_flag copy :1217-1224)
   FX_CUDA(cudaMemcpyAsync(t->stats_host, a.stats, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
@@ -592,7 +591,7 @@ int aspt_build(fx_tiles* t, cudaStream_t s) {
     FX_CUDA(cudaMemsetAsync(a.tcount, 0, sizeof(int) * (a.npanel + 1), s));
     static SmemAttr heavy_attr;
     if (int rc = heavy_attr.ensure(k_heavy, SORT_SMEM_CAP * sizeof(unsigned long long))) return rc;
-    k_heavy<<<a.G, 512, SORT_SMEM_CAP * sizeof(unsigned long long), s>>>(
+    k_heavy<<<a.G, build_threads(), SORT_SMEM_CAP * sizeof(unsigned long long), s>>>(
         a.csr_v, col, a.mcsr_chk, a.npanel, BW, min_occ, (int)m->n, a.cnt_scratch,
         reinterpret_cast<unsigned long long*>(a.heavy), a.nheavy, a.tcount, a.key2);
     FX_LAUNCH_CHECK();

@@ -105,7 +105,7 @@ __global__ void k_tcw_pad(const uint32_t* __restrict__ rowptr, int row0, int nlo
 }
 
 // stats: [3] panels dropped by the candidate cap, [5] total net gain (the rest is filled by k_tcw_panels)
-__global__ void __launch_bounds__(512) k_tcw_select(const int* __restrict__ csr_v, const uint32_t* __restrict__ col, int npanel,
+__global__ void __launch_bounds__(1024) k_tcw_select(const int* __restrict__ csr_v, const uint32_t* __restrict__ col, int npanel,
                                                     int ncols, int T, int W, int min_gain, int chunk_cost,
                                                     unsigned* __restrict__ cnt_all,
                                                     int* __restrict__ tc_cols, int* __restrict__ tc_ncol,
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(1024) k_tcw_panels(const int* __restrict__ tc_
 }
 
 // split of every row into its window part (chunk-major inside the panel) and its remainder (row order)
-__global__ void __launch_bounds__(512) k_tcw_split(const int* __restrict__ csr_v, const uint32_t* __restrict__ col,
+__global__ void __launch_bounds__(1024) k_tcw_split(const int* __restrict__ csr_v, const uint32_t* __restrict__ col,
                                                    const float* __restrict__ val, const int* __restrict__ win_rowptr,
                                                    const int* __restrict__ win_cptr, const int* __restrict__ tc_cols,
                                                    const int* __restrict__ tc_ncol, int npanel, int ncols, int W,
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(512) k_tcw_split(const int* __restrict__ csr_v
                                                    float* __restrict__ win_val, uint32_t* __restrict__ rest_col,
                                                    float* __restrict__ rest_val, unsigned long long* __restrict__ sched) {
   extern __shared__ int off2[];  // [CH][128] nz of (chunk, row), then their exclusive scan; then the listed-column table
-  __shared__ int wsum[16];
+  __shared__ int wsum[32];
   __shared__ int s_rp[BH + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(512) k_tcw_split(const int* __restrict__ csr_v
   int* s_cnt = reinterpret_cast<int*>(hk + HT);  // [nwarp][CH] window nz of a step per warp and chunk (long rows)
   int* s_run = s_cnt + nwarp * CH;               // [CH] window nz of the long row placed so far
   unsigned short* hs = reinterpret_cast<unsigned short*>(s_run + CH);
-  __shared__ int s_rest[16], s_rrest, s_next;
+  __shared__ int s_rest[32], s_rrest, s_next;
   constexpr int LONG_ROW = 512;
   __shared__ int s_panel;
   for (;;) {  // panels by a counter, as in k_tcw_select
@@ -570,7 +570,7 @@ int tcw_build(fx_tiles* t, cudaStream_t s) {
   const size_t hash_bytes = (size_t)tcw_hash_size(w.W) * (sizeof(unsigned) + sizeof(unsigned short));
   const size_t select_smem = CAND_CAP * sizeof(unsigned long long) + hash_bytes;
   if (int rc = select_attr.ensure(k_tcw_select, select_smem)) return rc;
-  k_tcw_select<<<a.G, 512, select_smem, s>>>(w.csr_v, col, a.npanel, (int)m->n, w.T, w.W, w.min_gain,
+  k_tcw_select<<<a.G, build_threads(), select_smem, s>>>(w.csr_v, col, a.npanel, (int)m->n, w.T, w.W, w.min_gain,
                                                                       w.chunk_cost, a.cnt_scratch, w.tc_cols, w.tc_ncol, w.win_len, w.chunk_len, w.stats);
   FX_LAUNCH_CHECK();
   {
@@ -586,10 +586,10 @@ int tcw_build(fx_tiles* t, cudaStream_t s) {
   FX_LAUNCH_CHECK();
   k_tcw_panels<<<1, 1024, 0, s>>>(w.tc_ncol, w.win_rowptr, a.npanel, a.nr, w.tc_panels, w.tc_slot, w.stats);
   FX_LAUNCH_CHECK();
-  const size_t split_smem = sizeof(int) * (size_t)(w.W / 32) * BH + hash_bytes + sizeof(int) * (size_t)(w.W / 32) * 17;
+  const size_t split_smem = sizeof(int) * (size_t)(w.W / 32) * BH + hash_bytes + sizeof(int) * (size_t)(w.W / 32) * 33;
   static SmemAttr split_attr;
   if (int rc = split_attr.ensure(k_tcw_split, split_smem)) return rc;
-  k_tcw_split<<<a.G, 512, split_smem, s>>>(w.csr_v, col, val, w.win_rowptr, w.win_cptr, w.tc_cols, w.tc_ncol, a.npanel, (int)m->n,
+  k_tcw_split<<<a.G, build_threads(), split_smem, s>>>(w.csr_v, col, val, w.win_rowptr, w.win_cptr, w.tc_cols, w.tc_ncol, a.npanel, (int)m->n,
                                            w.W, a.cnt_scratch, w.win_code, w.win_val, w.rest_col, w.rest_val, w.stats + 7);
   FX_LAUNCH_CHECK();
   // k_tcw_select leaves stale (epoch, count) words behind; the ASpT builder expects zeros (a streaming memset: 46 us for the

@@ -1,7 +1,6 @@
-bash scripts/r2_k2_profile.sh
-mkdir -p gpurun_out/r2_campaign
-for w in pubmed flickr; do for f in pillar seg tile; do
-timeout -s KILL 600 python bench.py --no-amazon --no-cpu-baseline --workload $w --k 128 --fmt $f --steps 100 2>gpurun_out/x.err | tail -1 > gpurun_out/r2_campaign/${w}_k128_$f.json
-python -c "
-import json; d=json.load(open('gpurun_out/r2_campaign/${w}_k128_$f.json')); print('$w k=128 $f', 'ms=%.4f GF=%.0f tPre=%.3f ratio=%.1f e2e=%.0f' % (d['ms_per_step'], d['value'], d['tPre_ms'], d['tPre_ms']/d['ms_per_step'], d['e2e']['value']))"
-done; done
+for cfg in "512 0 256" "1024 148 256" "1024 148 1024" "768 148 512" "512 296 1024"; do set -- $cfg
+  for w in "reddit " "reddit deg" "yelp deg" "amazon "; do set2=($w)
+    out=$(FLEX_BUILD_THREADS=$1 FLEX_BUILD_CTAS=$2 FLEX_DETECT_THREADS=$3 ORDER=${set2[1]} STEPS=3 WARM=1 timeout -s KILL 300 python scripts/r2_sweep.py ${set2[0]} 128 4:256:224:1024 2>&1 | tail -1 | sed 's/.*ntc/ntc/')
+    echo "threads=$1 ctas=$2 detect=$3 | ${set2[0]} ${set2[1]:-ovo} | $out"
+  done
+done
