@@ -586,10 +586,13 @@ int tcw_build(fx_tiles* t, cudaStream_t s) {
   FX_LAUNCH_CHECK();
   k_tcw_panels<<<1, 1024, 0, s>>>(w.tc_ncol, w.win_rowptr, a.npanel, a.nr, w.tc_panels, w.tc_slot, w.stats);
   FX_LAUNCH_CHECK();
+  // the split keeps no per-CTA counters, so its grid is its own: two 512-thread CTAs per SM (one of 1024 was slower, 0.74 vs
+  // 0.58 ms on Reddit-shape: its long-row steps synchronise the whole CTA); panels are handed out by a counter
+  const int split_ctas = std::min(2 * sm_count_of_current_device(), std::max(1, a.npanel));
   const size_t split_smem = sizeof(int) * (size_t)(w.W / 32) * BH + hash_bytes + sizeof(int) * (size_t)(w.W / 32) * 33;
   static SmemAttr split_attr;
   if (int rc = split_attr.ensure(k_tcw_split, split_smem)) return rc;
-  k_tcw_split<<<a.G, build_threads(), split_smem, s>>>(w.csr_v, col, val, w.win_rowptr, w.win_cptr, w.tc_cols, w.tc_ncol, a.npanel, (int)m->n,
+  k_tcw_split<<<split_ctas, 512, split_smem, s>>>(w.csr_v, col, val, w.win_rowptr, w.win_cptr, w.tc_cols, w.tc_ncol, a.npanel, (int)m->n,
                                            w.W, a.cnt_scratch, w.win_code, w.win_val, w.rest_col, w.rest_val, w.stats + 7);
   FX_LAUNCH_CHECK();
   // k_tcw_select leaves stale (epoch, count) words behind; the ASpT builder expects zeros (a streaming memset: 46 us for the
