@@ -635,8 +635,10 @@ int tcw_build(fx_tiles* t, cudaStream_t s) {
   const size_t hash_bytes = (size_t)tcw_hash_size(w.W) * (sizeof(unsigned) + sizeof(unsigned short));
   // the pass-1 table needs the whole SM's shared memory: only with one CTA per SM (the default, fx_common.cuh:build_threads)
   static const int h2_env = getenv("FLEX_SELECT_SMEM") ? atoi(getenv("FLEX_SELECT_SMEM")) : 1;
-  const int use_h2 = (h2_env && a.G <= sm_count_of_current_device()) ? 1 : 0;
-  const size_t select_smem = CAND_CAP * sizeof(unsigned long long) + hash_bytes + (use_h2 ? (size_t)HT2 * 8 : 0);
+  // (and only while it fits beside the candidate keys and the listed-column table: W = 4096 needs 48 KB for the latter)
+  const size_t select_base = CAND_CAP * sizeof(unsigned long long) + hash_bytes;
+  const int use_h2 = (h2_env && a.G <= sm_count_of_current_device() && select_base + (size_t)HT2 * 8 <= 216 * 1024) ? 1 : 0;
+  const size_t select_smem = select_base + (use_h2 ? (size_t)HT2 * 8 : 0);
   if (int rc = select_attr.ensure(k_tcw_select, select_smem)) return rc;
   k_tcw_select<<<a.G, build_threads(), select_smem, s>>>(w.csr_v, col, a.npanel, (int)m->n, w.T, w.W, w.min_gain,
                                                                       w.chunk_cost, a.cnt_scratch, w.tc_cols, w.tc_ncol, w.win_len, w.chunk_len, w.stats, use_h2);

@@ -48,7 +48,7 @@ def test_planted_blocks(orc, k):
 
 @pytest.mark.parametrize("T,W,min_gain,chunk_cost,min_total", [
     (2, 64, 1, 8, -1), (3, 32, 16, 40, -1), (8, 1024, 64, 224, -1), (4, 512, 100000, 224, -1), (4, 512, -1, -1, -1),
-    (4, 512, 64, 100, 30000), (4, 512, 64, 100, 10**9)])
+    (4, 512, 64, 100, 30000), (4, 512, 64, 100, 10**9), (4, 2048, 64, 100, -1), (4, 4096, 64, 100, -1)])
 def test_plan_parameters(orc, T, W, min_gain, chunk_cost, min_total):
     n, k = 1100, 64
     rp, c, v = random_csr(n, 9, 5, hubs=1, blocks=6)
