@@ -36,3 +36,6 @@ b amazon_k128 --workload amazon --k 128 --steps 20 --no-cpu-baseline
 b flickr_k128_pillar --workload flickr --k 128 --steps 50 --fmt pillar --no-cpu-baseline
 b flickr_k128_seg --workload flickr --k 128 --steps 50 --fmt seg --no-cpu-baseline
 b flickr_k128_tile --workload flickr --k 128 --steps 50 --fmt tile --no-cpu-baseline
+b pubmed_k128_pillar --workload pubmed --k 128 --steps 100 --fmt pillar --no-cpu-baseline
+b pubmed_k128_seg --workload pubmed --k 128 --steps 100 --fmt seg --no-cpu-baseline
+b pubmed_k128_tile --workload pubmed --k 128 --steps 100 --fmt tile --no-cpu-baseline

@@ -32,10 +32,10 @@ for name in order:
     open(os.path.join(ROOT, "profiles", "r2_campaign", name + ".json"), "w").write(json.dumps(d) + "\n")
 out += ["", "Notes.",
         "- Orderings feeding the tensor windows on Reddit-shape (VERDICT item 3-iv): Rabbit keeps 20 % of the nz in windows (natural planted-block order: 41 %) and is slower than the natural order",
-        "  (0.643 vs 0.536 ms) but faster than a shuffled labelling (0.702 -> 0.631 ms: it recovers half of the planted structure); DEG and RCM close every window (hub columns are spread over",
-        "  all panels, no panel shares enough columns) and DEG's hub-first panels cost the builder 24 ms (one CTA per panel walks 1.3 M nz: the builder's kernels do not split a panel).",
+        "  (0.638 vs 0.533 ms) but faster than a shuffled labelling (0.696 -> 0.625 ms: it recovers half of the planted structure); DEG and RCM close every window (hub columns are spread over",
+        "  all panels, no panel shares enough columns) and DEG's hub-first panels cost the builder 16 ms (one CTA per panel walks 1.3 M nz: the builder's kernels do not split a panel).",
         "- CPU arm on the same boxes (16 host threads, vectorised, whole matrix): 50-54 GFLOP/s pubmed k=32, 72-75 flickr-shape k=128, 65-69 Reddit-shape k=128.",
-        "- Flex formats (K2 consumers) at k=128, pillar / seg / tile: pubmed 259 / 782 / 515 GFLOP/s (the reference's own v36 kernel on the same box: 45-53), flickr-shape 1 714 / 828 / 493",
+        "- Flex formats (K2 consumers) at k=128, pillar / seg / tile: pubmed 273 / 792 / 518 GFLOP/s (the reference's own v36 kernel on the same box: 45-53), flickr-shape 1 732 / 828 / 492",
         "  (v36: 230-334; `r2_ref_flex_v36_context.log`). Round-2 changes to these kernels: the B rows of 8 nz requested before their FMAs (seg 0.56 -> 0.30 ms, tile 0.80 -> 0.51 on",
         "  flickr-shape) and, in the pillar kernel, the sweep over the other SMs' queues looks at 32 queues per step instead of visiting all 148 one by one (0.52 -> 0.145 ms).",
         "- Builds of the Flex formats (`scripts/r2_flex_tpre.py`, rebuilds): flickr-shape pillar 1.5 ms (49.3 all on the host -> 13.2 with rounds 2-3 on the GPU -> 2.0 with round 1 there too -> 1.5 sweeping a compacted remainder), seg 1.19, tile 1.50;",
