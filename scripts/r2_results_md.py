@@ -31,6 +31,8 @@ for name in order:
     os.makedirs(os.path.join(ROOT, "profiles", "r2_campaign"), exist_ok=True)
     open(os.path.join(ROOT, "profiles", "r2_campaign", name + ".json"), "w").write(json.dumps(d) + "\n")
 out += ["", "Notes.",
+        "- `frac xbar` is a MODEL (one 512-byte B row per gathered nz and per listed window column, plus the streams) over the port's 18.3 TB/s; where it exceeds 1 (ASpT layout, DEG order)",
+        "  L1 hits on hub columns served part of the modelled bytes -- ncu's count for the default configuration is 7.3 GB against the model's 7.9 GB.",
         "- Orderings feeding the tensor windows on Reddit-shape (VERDICT item 3-iv): Rabbit keeps 20 % of the nz in windows (natural planted-block order: 41 %) and is slower than the natural order",
         "  (0.638 vs 0.533 ms) but faster than a shuffled labelling (0.696 -> 0.625 ms: it recovers half of the planted structure); DEG and RCM close every window (hub columns are spread over",
         "  all panels, no panel shares enough columns) and DEG's hub-first panels cost the builder 16 ms (one CTA per panel walks 1.3 M nz: the builder's kernels do not split a panel).",
