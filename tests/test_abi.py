@@ -74,3 +74,25 @@ def test_reorder_with_rank_matches_oracle(orc):
     assert np.array_equal(d2.vo_mp, vo) and np.array_equal(r, rp2) and np.array_equal(cc, c2) and np.array_equal(vv, v2)
     with pytest.raises(fx.FlexError):
         dl.reorder_with_rank(np.zeros(n, np.uint64))
+
+
+def test_header_is_plain_c_and_struct_sizes_match(tmp_path):
+    """include/flexb200.h compiles as C11 (the boundary is a C ABI: no C++ in the signatures), and the ctypes mirrors of its
+    structs in flex_b200/__init__.py have the sizes the C compiler gives them."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc on this box")
+    names = {"fx_matrix_info": fx.MatrixInfo, "fx_build_opts": fx.BuildOpts, "fx_pillar_arrays": fx.PillarArrays, "fx_tcw_arrays": fx.TcwArrays,
+             "fx_seg_arrays": fx.SegArrays, "fx_tile_arrays": fx.TileArrays, "fx_aspt_arrays": fx.AsptArrays, "fx_report": fx.Report}
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "flexb200.h"\nint main(void) {\n' +
+                   "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    p = subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    for line in out.splitlines():
+        n, size = line.split()
+        assert C.sizeof(names[n]) == int(size), (n, C.sizeof(names[n]), size)
